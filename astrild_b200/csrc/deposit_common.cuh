@@ -1,0 +1,60 @@
+// Window kernels and mesh geometry shared by the deposit variants (pmesh semantics, see
+// deposit_atomic.cu for the reference citation).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace apk {
+
+struct DepositGeom {
+    int N;          // cells per side
+    int ldz;        // padded floats per z-row
+    double scale;   // grid units per position unit: pos_scale * N
+    double shift;   // affine shift in grid units (0.5 for the interlaced twin)
+    int slab;       // 0: whole periodic mesh, 1: slab with ghost planes
+    int plane0;     // global index of local plane 0 (x0 - ghost_lo), may be negative
+    int nplanes;    // local planes (ghost_lo + n0 + ghost_hi), == N when !slab
+
+    __host__ __device__ __forceinline__ int local_plane(long long ix) const;
+};
+
+__host__ __device__ __forceinline__ int wrap_index(long long i, int N) {
+    if ((unsigned long long)i < (unsigned long long)N) return (int)i;
+    if (i < 0 && i >= -(long long)N) return (int)(i + N);
+    if (i >= N && i < 2LL * N) return (int)(i - N);
+    long long r = i % N;
+    return (int)(r < 0 ? r + N : r);
+}
+
+__host__ __device__ __forceinline__ int DepositGeom::local_plane(long long ix) const {
+    const int gx = wrap_index(ix, N);
+    if (!slab) return gx;
+    int rel = gx - plane0;
+    if (rel < 0) rel += N;
+    else if (rel >= N) rel -= N;
+    return rel < nplanes ? rel : -1;
+}
+
+// base index and weights of pmesh's window of support S at grid coordinate g
+template <int S>
+__device__ __forceinline__ void window_1d(double g, long long &i0, float (&w)[S]) {
+    if (S == 1) {
+        i0 = (long long)floor(g + 0.5);
+        w[0] = 1.f;
+    } else if (S == 2) {
+        const double f = floor(g);
+        i0 = (long long)f;
+        const double d = g - f;
+        w[0] = (float)(1.0 - d);
+        w[S - 1] = (float)d;
+    } else {
+        const double f = floor(g + 0.5) - 1.0;
+        i0 = (long long)f;
+        const double dx = g - f;            // in [0.5, 1.5)
+        const double a = 1.5 - dx, b = dx - 1.0, c = dx - 0.5;
+        w[0] = (float)(0.5 * a * a);
+        w[S / 2] = (float)(0.75 - b * b);
+        w[S - 1] = (float)(0.5 * c * c);
+    }
+}
+
+}  // namespace apk

@@ -1,0 +1,282 @@
+"""PkEngine: one mesh geometry on one CUDA device, driving libastrild_pk.so.
+
+PyTorch is used for device memory, streams and host<->device copies only; every number is
+produced by the CUDA library.  Reference call sites this engine serves:
+  pm.paint / ArrayMesh / FFTPower in
+  /root/reference/src/astrild/particles/hutils/stats_subfind.py:125-150 and
+  /root/reference/src/astrild/power_spectra/power_spectrum_3d.py:164-226.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+from ._lib import AstrildPkError
+
+_ENGINES: dict = {}
+
+
+def get_engine(Nmesh: int, BoxSize: float, device=None) -> "PkEngine":
+    """Cached engine per (Nmesh, BoxSize, device): plans and buffers are reused across snapshots."""
+    dev = _resolve_device(device)
+    key = (int(Nmesh), float(BoxSize), dev.index)
+    eng = _ENGINES.get(key)
+    if eng is None:
+        eng = _ENGINES[key] = PkEngine(Nmesh, BoxSize, dev)
+    return eng
+
+
+def clear_engines() -> None:
+    for eng in list(_ENGINES.values()):
+        eng.close()
+    _ENGINES.clear()
+
+
+def _resolve_device(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise AstrildPkError("astrild_b200 needs a CUDA device: there is no CPU fallback for the P(k) path")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise AstrildPkError(f"astrild_b200 runs on CUDA devices only, got {dev}")
+    return torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+
+
+def _ptr(t):
+    return None if t is None else ct.c_void_p(t.data_ptr())
+
+
+@dataclass
+class Binning:
+    handle: ct.c_void_p
+    edges: np.ndarray
+    key: tuple
+
+
+class PkEngine:
+    def __init__(self, Nmesh: int, BoxSize: float, device=None, x0: int = 0, n0: int | None = None):
+        self.lib = _lib.load()
+        self.device = _resolve_device(device)
+        self.N = int(Nmesh)
+        self.L = float(BoxSize)
+        self.Nk = self.N // 2 + 1
+        self.ldz = 2 * self.Nk
+        self.x0 = int(x0)
+        self.n0 = self.N if n0 is None else int(n0)
+        self._plan = ct.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.call("apk_plan_create", ct.byref(self._plan), self.N, self.L, self.x0, self.n0, self.device.index)
+        lo, hi = ct.c_int(), ct.c_int()
+        _lib.call("apk_plan_ghost_planes", self._plan, ct.byref(lo), ct.byref(hi))
+        self.ghost_lo, self.ghost_hi = lo.value, hi.value
+        self._workspace = None
+        self._binnings: dict = {}
+        self._scratch = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.ensure_workspace(0, False)
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if self._plan:
+            for b in self._binnings.values():
+                self.lib.apk_binning_destroy(b.handle)
+            self._binnings.clear()
+            self.lib.apk_plan_destroy(self._plan)
+            self._plan = ct.c_void_p()
+            self._workspace = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self):
+        return ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ buffers
+    def new_mesh(self, ghosts: bool = False) -> torch.Tensor:
+        """float32 [planes][N][2*(N/2+1)]: the in-place r2c layout (ghost planes for slab deposits)."""
+        planes = self.n0 + (self.ghost_lo + self.ghost_hi if ghosts else 0)
+        return torch.empty((planes, self.N, self.ldz), dtype=torch.float32, device=self.device)
+
+    def ensure_workspace(self, max_particles: int, with_mass: bool) -> None:
+        need = ct.c_size_t()
+        _lib.call("apk_plan_workspace_bytes", self._plan, int(max_particles), int(with_mass), ct.byref(need))
+        if self._workspace is None or self._workspace.numel() < need.value:
+            self._workspace = None
+            self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
+            _lib.call("apk_plan_set_workspace", self._plan, _ptr(self._workspace), self._workspace.numel())
+
+    # ------------------------------------------------------------------ stage 1: deposit
+    def _positions(self, pos):
+        """-> (p0, p1, p2, layout, dtype, np, keepalive) on this device."""
+        if isinstance(pos, (tuple, list)) and len(pos) == 3 and not np.isscalar(pos[0]):
+            cols = [self._to_device(c).contiguous() for c in pos]
+            if not (cols[0].dtype == cols[1].dtype == cols[2].dtype):
+                raise AstrildPkError("SoA position columns must share one dtype")
+            if not (cols[0].ndim == 1 and cols[0].shape == cols[1].shape == cols[2].shape):
+                raise AstrildPkError("SoA position columns must be 1-D and equally long")
+            return cols[0], cols[1], cols[2], _lib.APK_SOA, cols[0].dtype, cols[0].shape[0], cols
+        t = self._to_device(pos)
+        if t.ndim != 2 or t.shape[1] != 3:
+            raise AstrildPkError(f"positions must be (Np, 3) or three (Np,) columns, got shape {tuple(t.shape)}")
+        t = t.contiguous()
+        return t, None, None, _lib.APK_AOS, t.dtype, t.shape[0], [t]
+
+    def _to_device(self, a) -> torch.Tensor:
+        t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(a))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t
+
+    def deposit(self, pos, mass=None, resampler: str = "tsc", shift: float = 0.0,
+                pos_scale: float | None = None, method: str = "auto", out: torch.Tensor | None = None,
+                zero: bool = True) -> torch.Tensor:
+        """pm.paint(pos, mass=mass, resampler=resampler) into a float32 mesh (mass per cell).
+
+        pos_scale: grid coordinate g = pos * pos_scale * N; default 1/BoxSize (positions in the
+        units of BoxSize); pass 1.0 for Ramses-style [0,1) coordinates.
+        """
+        rs = _lib.RESAMPLERS.get(str(resampler).lower())
+        if rs is None:
+            raise AstrildPkError(f"unknown resampler {resampler!r}")
+        p0, p1, p2, layout, dt, npart, keep = self._positions(pos)
+        m = None
+        if mass is not None and not np.isscalar(mass):
+            m = self._to_device(mass).contiguous()
+            if m.ndim != 1 or m.shape[0] != npart:
+                raise AstrildPkError("mass must be a scalar or have one entry per particle")
+        slab = self.n0 < self.N
+        if out is None:
+            out = self.new_mesh(ghosts=slab)
+        self.ensure_workspace(npart, m is not None)
+        _lib.call("apk_deposit", self._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout,
+                  _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64,
+                  float(1.0 / self.L if pos_scale is None else pos_scale), _ptr(m),
+                  _lib.APK_F32 if (m is None or m.dtype == torch.float32) else _lib.APK_F64,
+                  int(npart), rs, float(shift), _lib.DEPOSIT_METHODS[method], int(bool(zero)),
+                  _ptr(out), self.stream)
+        if mass is not None and np.isscalar(mass) and float(mass) != 1.0:
+            out.mul_(float(mass))
+        del keep
+        return out
+
+    # ------------------------------------------------------------------ stage 1': ArrayMesh
+    def load_mesh(self, array, subtract_mean: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Gridded field [n0][N][N] (float32/float64, host or device) -> float32 mesh.
+
+        The mean is removed in float64 before the cast: it only feeds the k = 0 mode, which
+        FFTPower zeroes, and removing it keeps the single-precision FFT clean of DC leakage.
+        """
+        t = self._to_device(array).contiguous()
+        if tuple(t.shape) != (self.n0, self.N, self.N):
+            raise AstrildPkError(f"value_map must have shape {(self.n0, self.N, self.N)}, got {tuple(t.shape)}")
+        dt = _lib.APK_F32 if t.dtype == torch.float32 else _lib.APK_F64
+        if out is None:
+            out = self.new_mesh()
+        mean = 0.0
+        if subtract_mean:
+            _lib.call("apk_mesh_sum", self._plan, _ptr(t), dt, _ptr(self._scratch), self.stream)
+            mean = float(self._scratch[0].item()) / (self.n0 * self.N * self.N)
+        _lib.call("apk_load_mesh", self._plan, _ptr(t), dt, mean, _ptr(out), self.stream)
+        return out
+
+    def mesh_sum(self, mesh: torch.Tensor) -> float:
+        """float64 sum over the real cells of a mesh (sum of deposited mass)."""
+        view = mesh[self.ghost_lo:self.ghost_lo + self.n0] if mesh.shape[0] != self.n0 else mesh
+        _lib.call("apk_padded_mesh_sum", self._plan, _ptr(view), _ptr(self._scratch), self.stream)
+        return float(self._scratch[0].item())
+
+    def store_mesh(self, mesh: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """mesh -> contiguous float64 [n0][N][N] * scale (what paint(...).value holds)."""
+        out = torch.empty((self.n0, self.N, self.N), dtype=torch.float64, device=self.device)
+        _lib.call("apk_store_mesh", self._plan, _ptr(mesh), float(scale), _ptr(out), self.stream)
+        return out
+
+    # ------------------------------------------------------------------ stage 2: r2c
+    def r2c(self, mesh: torch.Tensor) -> torch.Tensor:
+        """In-place un-normalised r2c; returns the complex64 [N][N][N/2+1] view of the same memory."""
+        if self.n0 != self.N:
+            raise AstrildPkError("r2c on a slab engine: use astrild_b200.distributed")
+        _lib.call("apk_fft_r2c", self._plan, _ptr(mesh), self.stream)
+        return torch.view_as_complex(mesh.view(self.N, self.N, self.Nk, 2))
+
+    # ------------------------------------------------------------------ stage 3: binning
+    def binning(self, kmin: float = 0.0, dk: float | None = None, kmax: float | None = None,
+                compensation: tuple | None = None, interlaced: bool = False, k_dtype=np.float64,
+                axes=None) -> Binning:
+        """Binning tables for FFTPower(mode='1d', kmin, dk, kmax).
+
+        compensation: None or (resampler, interlaced_flag) selecting nbodykit's Compensate* factor.
+        axes: None for the single-GPU [x][y][z] grid, or (a_index_array, b_index_array, dc_a, dc_b,
+        n_a, n_b, ka, kb) for a transposed slab (see distributed.py).
+        """
+        key = (float(kmin), dk, kmax, compensation, bool(interlaced), np.dtype(k_dtype).str,
+               None if axes is None else axes["key"])
+        b = self._binnings.get(key)
+        if b is not None:
+            return b
+        N, L = self.N, self.L
+        kfull = tables.k_axis(N, L, k_dtype)
+        edges = tables.k_edges(N, L, kmin, dk, kmax)
+        if len(edges) < 2:
+            raise AstrildPkError("binning needs at least two k edges")
+        kz = np.ascontiguousarray(kfull[: self.Nk])
+        wz = np.ascontiguousarray(tables.hermitian_weights(N))
+        if axes is None:
+            ia = ib = np.arange(N)
+        else:
+            ia, ib = axes["ia"], axes["ib"]
+        ka = np.ascontiguousarray(kfull[ia])
+        kb = np.ascontiguousarray(kfull[ib])
+        dc_a = int(np.flatnonzero(ia == 0)[0]) if (ia == 0).any() else -1
+        dc_b = int(np.flatnonzero(ib == 0)[0]) if (ib == 0).any() else -1
+        comp = [None] * 3
+        if compensation is not None:
+            c = tables.compensation_axis(compensation[0], bool(compensation[1]), N)
+            comp = [np.ascontiguousarray(c[ia]), np.ascontiguousarray(c[ib]), np.ascontiguousarray(c[: self.Nk])]
+        ph = [None] * 3
+        if interlaced:
+            p = tables.interlace_phase_axis(N, L)
+            ph = [np.ascontiguousarray(p[ia]), np.ascontiguousarray(p[ib]), np.ascontiguousarray(p[: self.Nk])]
+
+        def hp(a):
+            return None if a is None else a.ctypes.data_as(ct.c_void_p)
+
+        handle = ct.c_void_p()
+        _lib.call("apk_binning_create", ct.byref(handle), self._plan, len(ka), len(kb), len(kz),
+                  hp(ka), hp(kb), hp(kz), hp(wz), hp(edges), len(edges),
+                  hp(comp[0]), hp(comp[1]), hp(comp[2]), hp(ph[0]), hp(ph[1]), hp(ph[2]), dc_a, dc_b)
+        b = Binning(handle, edges, key)
+        self._binnings[key] = b
+        return b
+
+    def bin_power_raw(self, binning: Binning, c1, c1s=None, c2=None, c2s=None) -> torch.Tensor:
+        """Raw shell sums on the device: float64 [4][nedges+1] = ksum, psum_re, psum_im, nmodes(int64 bits)."""
+        nb1 = len(binning.edges) + 1
+        out = torch.empty((4, nb1), dtype=torch.float64, device=self.device)
+        _lib.call("apk_bin_power", binning.handle, _ptr(c1), _ptr(c1s), _ptr(c2), _ptr(c2s),
+                  _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(out[3]), self.stream)
+        return out
+
+    @staticmethod
+    def finish(raw: torch.Tensor, binning: Binning, scale: float) -> dict:
+        """Device sums -> host arrays with nbodykit's conventions (project_to_basis tail)."""
+        host = raw.cpu().numpy()
+        nsum = host[3].view(np.int64).copy()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            k = (host[0] / nsum)[1:-1]
+            power = ((host[1] + 1j * host[2]) * scale / nsum)[1:-1]
+        return {"k": k, "power": power, "modes": nsum[1:-1].copy(), "edges": binning.edges,
+                "Nsum": nsum}
+
+    def bin_power(self, binning: Binning, c1, c1s=None, c2=None, c2s=None, scale: float = 1.0) -> dict:
+        return self.finish(self.bin_power_raw(binning, c1, c1s, c2, c2s), binning, scale)

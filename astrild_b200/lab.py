@@ -1,0 +1,233 @@
+"""The slice of ``nbodykit.lab`` / ``pmesh.pm`` that astrild's P(k) path uses, on the B200.
+
+astrild does ``from nbodykit.lab import *`` and ``import pmesh`` and then calls exactly
+  pmesh.pm.ParticleMesh(Nmesh=[n]*3, BoxSize=L).paint(pos, mass=m, resampler="tsc")
+        /root/reference/src/astrild/particles/hutils/stats_subfind.py:130-132
+  ArrayMesh(value_map, Nmesh=n, compensated=..., interlaced=..., window=..., BoxSize=L)
+        /root/reference/src/astrild/power_spectra/power_spectrum_3d.py:183-188, 197-212
+  FFTPower(first, mode="1d", second=..., kmin=2*pi/L) -> r.power["k"|"power"|"modes"], r.power.attrs["shotnoise"]
+        /root/reference/src/astrild/power_spectra/power_spectrum_3d.py:189-195, 216-224
+Same names, same arguments, same returned arrays; the arithmetic runs in libastrild_pk.so.
+
+Semantics kept from nbodykit:
+  * ArrayMesh only STORES compensated/interlaced/window in attrs; nothing is deconvolved or
+    interlaced for a gridded field, and its shotnoise is 0.
+  * CatalogMesh (particles) is where resampler / interlaced / compensated act.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine as _engine
+from ._lib import AstrildPkError
+
+
+def _box3(BoxSize) -> float:
+    b = np.atleast_1d(np.asarray(BoxSize, dtype=np.float64))
+    if not np.all(b == b[0]):
+        raise AstrildPkError("only cubic boxes are supported (astrild passes a scalar BoxSize)")
+    return float(b[0])
+
+
+def _nmesh(Nmesh) -> int:
+    n = np.atleast_1d(np.asarray(Nmesh))
+    if not np.all(n == n[0]):
+        raise AstrildPkError("only cubic meshes are supported (astrild passes Nmesh=[n]*3 or n)")
+    return int(n[0])
+
+
+class RealField:
+    """What ``pm.paint`` returns: ``.value`` is the (N,N,N) float64 array of mass per cell."""
+
+    def __init__(self, eng, mesh, scale: float = 1.0):
+        self._eng, self._mesh, self._scale = eng, mesh, scale
+        self._value = None
+
+    @property
+    def value(self) -> np.ndarray:
+        if self._value is None:
+            self._value = self._eng.store_mesh(self._mesh, self._scale).cpu().numpy()
+        return self._value
+
+    @property
+    def device_mesh(self) -> torch.Tensor:
+        """The float32 padded device mesh (zero-copy hand-over to ArrayMesh / FFTPower)."""
+        return self._mesh
+
+    def __truediv__(self, s):
+        return RealField(self._eng, self._mesh, self._scale / float(s))
+
+    def __mul__(self, s):
+        return RealField(self._eng, self._mesh, self._scale * float(s))
+
+    __rmul__ = __mul__
+
+    def csum(self) -> float:
+        return self._eng.mesh_sum(self._mesh) * self._scale
+
+
+class ParticleMesh:
+    """``pmesh.pm.ParticleMesh(Nmesh=[n]*3, BoxSize=L)`` with ``paint``."""
+
+    def __init__(self, Nmesh, BoxSize=1.0, dtype="f8", resampler="cic", device=None, **_ignored):
+        self.Nmesh = np.array([_nmesh(Nmesh)] * 3)
+        self.BoxSize = np.array([_box3(BoxSize)] * 3)
+        self.resampler = resampler
+        self._eng = _engine.get_engine(int(self.Nmesh[0]), float(self.BoxSize[0]), device)
+
+    def paint(self, pos, mass=1.0, resampler=None, hold=False, out=None, shift: float = 0.0,
+              method: str = "auto") -> RealField:
+        m = None if (np.isscalar(mass) and float(mass) == 1.0) else mass
+        mesh = self._eng.deposit(pos, m, resampler or self.resampler, shift=shift, method=method,
+                                 out=None if out is None else out.device_mesh, zero=not hold)
+        return RealField(self._eng, mesh)
+
+
+class ArrayMesh:
+    """``nbodykit.lab.ArrayMesh(array, BoxSize, **kwargs)``: a gridded field as a mesh source.
+
+    ``array`` may be a NumPy array, a torch tensor, or the RealField that ``paint`` returned
+    (possibly divided by dx**3) -- the latter stays on the device.
+    """
+
+    def __init__(self, array, BoxSize, comm=None, root=0, device=None, **kwargs):
+        self.attrs = dict(kwargs)
+        L = _box3(BoxSize)
+        self.attrs["BoxSize"] = np.array([L] * 3)
+        self._field_scale = 1.0
+        if isinstance(array, RealField):
+            self._eng = array._eng
+            self._real = array
+            self._array = None
+            N = self._eng.N
+            if self._eng.L != L:
+                raise AstrildPkError("ArrayMesh BoxSize differs from the ParticleMesh that painted the field")
+        else:
+            a = array if isinstance(array, torch.Tensor) else np.asarray(array)
+            if a.ndim != 3 or not (a.shape[0] == a.shape[1] == a.shape[2]):
+                raise AstrildPkError(f"ArrayMesh needs a cubic 3-D array, got shape {tuple(a.shape)}")
+            if np.iscomplexobj(a) if not isinstance(a, torch.Tensor) else a.is_complex():
+                raise AstrildPkError("complex input to ArrayMesh is not supported on this path")
+            N = int(a.shape[0])
+            self._eng = _engine.get_engine(N, L, device)
+            self._array = a
+            self._real = None
+        self.attrs["Nmesh"] = np.array([N] * 3)
+
+    # the device mesh ready for the r2c, and the scalar the field must be multiplied by
+    def _to_device_mesh(self):
+        if self._real is not None:
+            # FFT is in place: work on a copy so the painted field stays valid
+            return self._real.device_mesh.clone(), self._real._scale
+        return self._eng.load_mesh(self._array), 1.0
+
+    def _complex_fields(self):
+        mesh, scale = self._to_device_mesh()
+        return (self._eng.r2c(mesh), None), scale, None
+
+    shotnoise = 0.0
+    N_attr = 0
+
+
+class CatalogMesh:
+    """Particles as a mesh source with nbodykit's CatalogMesh options.
+
+    position: (Np,3) or three (Np,) columns in the units of BoxSize; weight: per-particle mass.
+    normalize=True gives 1 + delta (field / mean); normalize=False keeps rho = mass / dx^3,
+    which is what astrild's SubFind.power_spectrum feeds to FFTPower.
+    """
+
+    def __init__(self, position, BoxSize, Nmesh, weight=None, resampler="cic", interlaced=False,
+                 compensated=False, normalize=True, pos_scale=None, device=None, method="auto"):
+        self.attrs = {"BoxSize": np.array([_box3(BoxSize)] * 3), "Nmesh": np.array([_nmesh(Nmesh)] * 3),
+                      "resampler": resampler, "interlaced": bool(interlaced), "compensated": bool(compensated)}
+        self._eng = _engine.get_engine(_nmesh(Nmesh), _box3(BoxSize), device)
+        self._pos, self._w = position, weight
+        self._normalize, self._pos_scale, self._method = bool(normalize), pos_scale, method
+        if compensated and str(resampler).lower() not in ("cic", "tsc"):
+            raise AstrildPkError("compensated=True needs resampler 'cic' or 'tsc'")
+
+    def _complex_fields(self):
+        eng, a = self._eng, self.attrs
+        mesh = eng.deposit(self._pos, self._w, a["resampler"], 0.0, self._pos_scale, self._method)
+        total = eng.mesh_sum(mesh) if self._normalize else None
+        mesh_s = None
+        if a["interlaced"]:
+            mesh_s = eng.deposit(self._pos, self._w, a["resampler"], 0.5, self._pos_scale, self._method)
+        if self._normalize:
+            scale = eng.N ** 3 / total
+        else:
+            scale = 1.0 / (eng.L / eng.N) ** 3
+        c = eng.r2c(mesh)
+        cs = eng.r2c(mesh_s) if mesh_s is not None else None
+        comp = (str(a["resampler"]).lower(), a["interlaced"]) if a["compensated"] else None
+        return (c, cs), scale, comp
+
+
+class BinnedStatistic:
+    """Minimal stand-in for nbodykit's BinnedStatistic: ``obj["k"]``, ``.attrs``, ``.edges``."""
+
+    def __init__(self, dims, edges, data: dict, attrs: dict):
+        self.dims = list(dims)
+        self.edges = dict(zip(dims, edges))
+        self.data = data
+        self.attrs = attrs
+        self.shape = (len(edges[0]) - 1,)
+        self.variables = list(data)
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def __contains__(self, key):
+        return key in self.data
+
+    def __iter__(self):
+        return iter(self.data)
+
+
+class FFTPower:
+    """``FFTPower(first, mode='1d', second=None, kmin=0., dk=None, kmax=None)``.
+
+    Result in ``self.power`` with variables ``k`` (mean |k| of the modes in the bin, NaN if
+    empty), ``power`` (complex; real part is P(k)), ``modes`` (int64) and attrs including
+    ``shotnoise`` (0 for ArrayMesh input, V*sum(w^2)/sum(w)^2 is NOT computed here: astrild
+    only ever feeds ArrayMesh).
+    """
+
+    def __init__(self, first, mode="1d", Nmesh=None, BoxSize=None, second=None, los=(0, 0, 1),
+                 Nmu=None, dk=None, kmin=0.0, kmax=None, poles=None, k_dtype=np.float64):
+        if mode != "1d":
+            raise AstrildPkError("only mode='1d' is implemented (the only mode astrild uses)")
+        if poles:
+            raise AstrildPkError("multipoles are not implemented on this path")
+        eng = first._eng
+        if second is not None and second is not first and second._eng is not eng:
+            raise AstrildPkError("first and second must share Nmesh, BoxSize and device")
+        self.first, self.second = first, first if second is None else second
+        N, L = eng.N, eng.L
+        (c1, c1s), s1, comp1 = first._complex_fields()
+        if second is None or second is first:
+            c2 = c2s = None
+            s2, comp2 = s1, comp1
+        else:
+            (c2, c2s), s2, comp2 = second._complex_fields()
+            if (c1s is None) != (c2s is None):
+                raise AstrildPkError("first and second must both be interlaced or both not")
+            if comp1 != comp2:
+                raise AstrildPkError("first and second must use the same window compensation")
+        binning = eng.binning(kmin, dk, kmax, comp1, c1s is not None, k_dtype)
+        scale = L ** 3 * s1 * s2 / float(N) ** 6
+        res = eng.bin_power(binning, c1, c1s, c2, c2s, scale)
+        edges = binning.edges
+        self.attrs = {"mode": mode, "Nmesh": np.array([N] * 3), "BoxSize": np.array([L] * 3),
+                      "dk": 2 * np.pi / L if dk is None else dk, "kmin": kmin, "kmax": kmax,
+                      "Nmu": 1, "los": list(los), "poles": [], "volume": L ** 3,
+                      "shotnoise": 0.0, "N1": 0, "N2": 0}
+        self.power = BinnedStatistic(["k"], [edges], {"k": res["k"], "power": res["power"],
+                                                      "modes": res["modes"]}, dict(self.attrs))
+        self.poles = None
+        self._Nsum = res["Nsum"]
+
+    def run(self):
+        return self.power, None

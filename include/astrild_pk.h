@@ -1,0 +1,123 @@
+/* astrild_pk.h -- C ABI of libastrild_pk.so: the B200 (sm_100a) implementation of astrild's
+ * matter/halo power-spectrum hot path (particle->mesh deposit, r2c 3-D FFT, |delta(k)|^2 shell
+ * binning with mode counts).
+ *
+ * astrild has no FFI for this path: it calls pmesh / nbodykit from Python.  Each entry point
+ * below names the reference call it replaces (paths relative to /root/reference):
+ *
+ *   apk_deposit        pm.paint(pos, mass=, resampler=)           src/astrild/particles/hutils/stats_subfind.py:130-131
+ *   apk_load_mesh      ArrayMesh(value_map, BoxSize=, ...)         src/astrild/power_spectra/power_spectrum_3d.py:183-188, 197-212
+ *   apk_fft_r2c        FFTPower -> mesh.compute('complex') (r2c)  src/astrild/power_spectra/power_spectrum_3d.py:189-195
+ *   apk_bin_power      FFTPower(mode="1d", kmin=) binning         src/astrild/power_spectra/power_spectrum_3d.py:189-195, 216-222;
+ *                                                                  src/astrild/particles/hutils/stats_subfind.py:142-148
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; apk_last_error() gives the
+ *     message of the calling thread's last failure.  (The repo's only native precedent,
+ *     src/astrild/rays/skys/sky_utils.py:402-435, has no error channel; this one does.)
+ *   - all data pointers are DEVICE pointers unless the parameter name ends in _host.
+ *   - the caller owns every buffer (particles, meshes, outputs, workspace); a plan owns only
+ *     its cuFFT handle and small device tables.  A plan is bound to one device and must not
+ *     be used from two host threads at once.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *   - a "mesh" is the in-place r2c layout: float[n0][N][2*(N/2+1)], last axis padded; after
+ *     apk_fft_r2c the same memory holds complex64[n0][N][N/2+1] (un-normalised cuFFT output;
+ *     the 1/N^3 of pmesh's r2c is folded into the scale the host applies to the shell sums).
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef ASTRILD_PK_H
+#define ASTRILD_PK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APK_VERSION 100
+
+typedef struct apk_plan apk_plan;
+typedef struct apk_binning apk_binning;
+
+enum { APK_F32 = 0, APK_F64 = 1 };
+enum { APK_AOS = 0, APK_SOA = 1 };                     /* (Np,3) array or three (Np,) arrays   */
+enum { APK_NGP = 1, APK_CIC = 2, APK_TSC = 3 };        /* = window support, pmesh resamplers   */
+enum { APK_DEPOSIT_AUTO = 0, APK_DEPOSIT_ATOMIC = 1, APK_DEPOSIT_SORTED = 2 };
+
+int apk_version(void);
+const char *apk_last_error(void);
+
+/* ---- plan: one mesh geometry on one device ------------------------------------------------ */
+/* nmesh = N cells per side (pmesh Nmesh=[N]*3), boxsize = L.  n0/x0: this rank's slab of mesh
+ * planes along axis 0 (single GPU: x0 = 0, n0 = N).                                           */
+int apk_plan_create(apk_plan **plan, int nmesh, double boxsize, int x0, int n0, int device);
+int apk_plan_destroy(apk_plan *plan);
+/* floats in one local mesh: n0 * N * 2*(N/2+1)                                               */
+int apk_plan_mesh_elems(const apk_plan *plan, int64_t *elems);
+/* bytes of scratch apk_deposit (sorted path, max_particles) and apk_fft_r2c need            */
+int apk_plan_workspace_bytes(const apk_plan *plan, int64_t max_particles, int with_mass, size_t *bytes);
+int apk_plan_set_workspace(apk_plan *plan, void *workspace, size_t bytes);
+/* slab plans deposit into n_lo + n0 + n_hi planes (ghosts below/above the owned slab, to be
+ * sent to and added by the ring neighbours); single-GPU plans report 0, 0.                    */
+int apk_plan_ghost_planes(const apk_plan *plan, int *n_lo, int *n_hi);
+
+/* ---- deposit (pm.paint) ------------------------------------------------------------------- */
+/* Adds mass * W(cell - g) to `mesh` for every particle, g = pos * pos_scale * N + shift (grid
+ * units; cell i is centred on g = i), periodic.  pos_scale = 1/L for positions in box-length
+ * units of L, 1 for Ramses-style [0,1) coordinates.  layout APK_AOS: p0 -> (Np,3), p1 = p2 = 0;
+ * APK_SOA: p0,p1,p2 -> x,y,z.  mass may be NULL (unit mass).  shift = 0.5 paints the
+ * interlaced twin.  zero_first != 0 clears the mesh before accumulating.
+ * Slab plans (n0 < N): `mesh` has n_lo + n0 + n_hi planes (apk_plan_ghost_planes), plane 0 is
+ * global plane x0 - n_lo; every particle must have floor(g_x - shift) in [x0, x0+n0).
+ * Single-GPU plans wrap periodically.                                                        */
+int apk_deposit(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
+                int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
+                int resampler, double shift, int method, int zero_first, float *mesh, void *stream);
+
+/* ---- ArrayMesh: gridded field -> mesh ------------------------------------------------------ */
+/* value_map: contiguous [n0][N][N] of dtype; writes (value - mean_subtract) as f32 into the
+ * padded mesh.  apk_mesh_sum gives the f64 sum of a value_map (for the mean).                 */
+int apk_mesh_sum(apk_plan *plan, const void *value_map, int dtype, double *sum_dev, void *stream);
+int apk_load_mesh(apk_plan *plan, const void *value_map, int dtype, double mean_subtract,
+                  float *mesh, void *stream);
+/* the reverse: padded f32 mesh -> contiguous [n0][N][N] doubles, times scale (paint().value)  */
+int apk_store_mesh(apk_plan *plan, const float *mesh, double scale, double *value_map, void *stream);
+/* f64 sum over the N^3 real cells of a padded mesh (Sum mass; nbar for normalisation)         */
+int apk_padded_mesh_sum(apk_plan *plan, const float *mesh, double *sum_dev, void *stream);
+
+/* ---- r2c ----------------------------------------------------------------------------------- */
+/* in-place, un-normalised, single precision; single-GPU plans only (slab plans run the
+ * 2-D + transpose + 1-D stages from the host side, see astrild_b200/distributed.py).          */
+int apk_fft_r2c(apk_plan *plan, float *mesh, void *stream);
+/* slab stages: batched 2-D r2c over (y,z) of n0 local planes, and batched 1-D c2c along the
+ * leading axis of a [N][ny_local][N/2+1] array.                                              */
+int apk_fft_r2c_2d(apk_plan *plan, float *mesh, void *stream);
+int apk_fft_c2c_1d(apk_plan *plan, void *grid, int ny_local, void *stream);
+
+/* ---- binning (FFTPower mode="1d") ---------------------------------------------------------- */
+/* The k-grid is complex64 [n_a][n_b][nz] (nz = N/2+1).  k2 = (ka2[ia] + kb2[ib]) + kz2[iz] in
+ * float64, tables = squares of the HOST-built per-axis k tables (so the host decides their
+ * dtype/expression); bin = numpy.digitize(k2, kedges2).
+ * wz[iz] is the Hermitian weight (2 where k_z > 0 else 1).  Optional per-axis tables:
+ * comp_* = factor the complex field is DIVIDED by (window compensation), phase_* = radians of
+ * the interlacing phase 0.5*k_i*H.  dc_a/dc_b = local indices of the k=0 row (or -1).         */
+int apk_binning_create(apk_binning **binning, apk_plan *plan, int n_a, int n_b, int nz,
+                       const double *ka_host, const double *kb_host, const double *kz_host,
+                       const double *wz_host, const double *kedges_host, int nedges,
+                       const double *comp_a_host, const double *comp_b_host, const double *comp_z_host,
+                       const double *phase_a_host, const double *phase_b_host, const double *phase_z_host,
+                       int dc_a, int dc_b);
+int apk_binning_destroy(apk_binning *binning);
+/* c1: field 1; c1s: its interlaced twin or NULL; c2/c2s: second field for a cross spectrum or
+ * NULL.  Outputs have nedges+1 entries (numpy.digitize indices 0..nedges: under/overflow
+ * included) and are OVERWRITTEN: ksum = sum w*sqrt(k2), psum_re = sum w*Re(c1 conj c2),
+ * psum_im = sum Im(c1 conj c2) over singular planes only, nmodes = sum w.                     */
+int apk_bin_power(apk_binning *binning, const void *c1, const void *c1s, const void *c2,
+                  const void *c2s, double *ksum, double *psum_re, double *psum_im,
+                  int64_t *nmodes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASTRILD_PK_H */
