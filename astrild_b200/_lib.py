@@ -35,6 +35,9 @@ SIGNATURES = {
     "apk_plan_workspace_bytes": [_vp, _i64, _i, ct.POINTER(_sz)],
     "apk_plan_set_workspace": [_vp, _vp, _sz],
     "apk_plan_ghost_planes": [_vp, ct.POINTER(_i), ct.POINTER(_i)],
+    "apk_plan_enable_timing": [_vp, _i],
+    "apk_plan_last_deposit_ms": [_vp, ct.POINTER(ct.c_float)],
+    "apk_binning_last_ms": [_vp, ct.POINTER(ct.c_float)],
     "apk_deposit": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _d, _i, _i, _vp, _vp],
     "apk_mesh_sum": [_vp, _vp, _i, _vp, _vp],
     "apk_padded_mesh_sum": [_vp, _vp, _vp, _vp],

@@ -117,6 +117,7 @@ int apk_plan_destroy(apk_plan *P) {
     if (P->has_fft2d) cufftDestroy(P->fft2d);
     if (P->has_fft1d) cufftDestroy(P->fft1d);
     if (P->scratch) cudaFree(P->scratch);
+    if (P->ev_ready) for (auto &e : P->ev) cudaEventDestroy(e);
     delete P;
     return 0;
 }
@@ -166,9 +167,44 @@ int apk_deposit(apk_plan *P, const void *p0, const void *p1, const void *p2, int
         APK_CUDA(cudaMemsetAsync(mesh, 0, sizeof(float) * (size_t)G.nplanes * P->N * P->ldz, st));
     if (method == APK_DEPOSIT_AUTO)
         method = (np >= (1 << 18)) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
-    if (method == APK_DEPOSIT_SORTED)
+    P->dep_timed = false;
+    if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
         return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, st);
-    return deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
+    if (P->mark(3, st)) { set_error("apk_deposit: event record failed"); return 1; }
+    int rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
+    if (rc) return rc;
+    if (P->mark(4, st)) { set_error("apk_deposit: event record failed"); return 1; }
+    P->dep_timed = P->timing;
+    P->dep_sorted = false;
+    return 0;
+}
+
+int apk_plan_enable_timing(apk_plan *P, int on) {
+    APK_REQUIRE(P, "apk_plan_enable_timing: null plan");
+    P->timing = on != 0;
+    return 0;
+}
+
+int apk_plan_last_deposit_ms(apk_plan *P, float ms[4]) {
+    APK_REQUIRE(P && ms, "apk_plan_last_deposit_ms: null argument");
+    APK_REQUIRE(P->dep_timed, "apk_plan_last_deposit_ms: no timed deposit on this plan (apk_plan_enable_timing)");
+    DeviceGuard guard(P->device);
+    APK_CUDA(cudaEventSynchronize(P->ev[4]));
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (P->dep_sorted)
+        for (int i = 0; i < 3; ++i) APK_CUDA(cudaEventElapsedTime(&ms[i], P->ev[i], P->ev[i + 1]));
+    APK_CUDA(cudaEventElapsedTime(&ms[3], P->ev[3], P->ev[4]));
+    return 0;
+}
+
+int apk_binning_last_ms(apk_binning *B, float ms[2]) {
+    APK_REQUIRE(B && ms, "apk_binning_last_ms: null argument");
+    APK_REQUIRE(B->timed, "apk_binning_last_ms: no timed apk_bin_power on this binning (apk_plan_enable_timing)");
+    DeviceGuard guard(B->plan->device);
+    APK_CUDA(cudaEventSynchronize(B->ev[2]));
+    APK_CUDA(cudaEventElapsedTime(&ms[0], B->ev[0], B->ev[1]));
+    APK_CUDA(cudaEventElapsedTime(&ms[1], B->ev[1], B->ev[2]));
+    return 0;
 }
 
 int apk_mesh_sum(apk_plan *P, const void *value_map, int dtype, double *sum_dev, void *stream) {
@@ -313,6 +349,7 @@ int apk_binning_destroy(apk_binning *B) {
     DeviceGuard guard(B->plan->device);
     if (B->tables) cudaFree(B->tables);
     if (B->partial) cudaFree(B->partial);
+    if (B->ev_ready) for (auto &e : B->ev) cudaEventDestroy(e);
     delete B;
     return 0;
 }

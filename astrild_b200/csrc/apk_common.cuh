@@ -65,6 +65,20 @@ struct apk_plan {
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
     double *scratch = nullptr;   // small device scratch for reductions (plan-owned)
+    bool timing = false;
+    cudaEvent_t ev[6] = {};      // deposit: 0..4, created on first use
+    bool ev_ready = false;
+    bool dep_timed = false;      // events of the last deposit are valid
+    bool dep_sorted = false;
+
+    int mark(int i, cudaStream_t st) {
+        if (!timing) return 0;
+        if (!ev_ready) {
+            for (auto &e : ev) if (cudaEventCreate(&e) != cudaSuccess) return 1;
+            ev_ready = true;
+        }
+        return cudaEventRecord(ev[i], st) != cudaSuccess;
+    }
 };
 
 struct apk_binning {
@@ -82,4 +96,6 @@ struct apk_binning {
     // per-CTA private partial histograms (plan-lifetime allocation)
     double *partial = nullptr;
     int partial_ctas = 0;
+    cudaEvent_t ev[3] = {};
+    bool ev_ready = false, timed = false;
 };

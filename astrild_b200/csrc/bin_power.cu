@@ -305,6 +305,12 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
 
     const size_t smem = bin_smem_bytes(B->nedges);
     const bool comp = B->has_comp;
+    const bool timing = B->plan->timing;
+    if (timing && !B->ev_ready) {
+        for (auto &e : B->ev) APK_CUDA(cudaEventCreate(&e));
+        B->ev_ready = true;
+    }
+    if (timing) APK_CUDA(cudaEventRecord(B->ev[0], st));
     int rc;
     if (interlaced) {
         if (cross) rc = comp ? launch_bin<true, true, true>(A, ctas, smem, st) : launch_bin<true, true, false>(A, ctas, smem, st);
@@ -314,9 +320,12 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
         else rc = comp ? launch_bin<false, false, true>(A, ctas, smem, st) : launch_bin<false, false, false>(A, ctas, smem, st);
     }
     if (rc) return rc;
+    if (timing) APK_CUDA(cudaEventRecord(B->ev[1], st));
     bin_fold_kernel<<<(nb1 + 127) / 128, 128, 0, st>>>(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1,
                                                       ksum, psum_re, psum_im, (long long *)nmodes);
     APK_CUDA(cudaGetLastError());
+    if (timing) APK_CUDA(cudaEventRecord(B->ev[2], st));
+    B->timed = timing;
     return 0;
 }
 

@@ -350,11 +350,14 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     size_t cub_bytes = P->workspace_bytes - (size_t)(w - (unsigned char *)P->workspace);
 
     const int kb = (int)std::min<long long>((np + 255) / 256, (long long)P->num_sms * 16);
+    P->mark(0, st);
     brick_key_kernel<S, PT, SOA, MASS, VT><<<kb, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass,
                                                               mass_dtype == APK_F64, np, G, B, keys_a, vals_a);
     APK_CUDA(cudaGetLastError());
+    P->mark(1, st);
     APK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const unsigned int *)keys_a, keys_b,
                                              (const VT *)vals_a, vals_b, np, 0, B.bits, st));
+    P->mark(2, st);
     brick_bounds_kernel<<<(B.nbricks + 1 + 255) / 256, 256, 0, st>>>(keys_b, np, B.nbricks, brick_start);
     APK_CUDA(cudaGetLastError());
     APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
@@ -366,8 +369,12 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     APK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEP_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
     const int ctas = std::min(P->num_sms * per_sm, B.nbricks);
+    P->mark(3, st);
     kern<<<ctas, DEP_THREADS, smem, st>>>(vals_b, brick_start, G, B, counter, mesh);
     APK_CUDA(cudaGetLastError());
+    P->mark(4, st);
+    P->dep_timed = P->timing;
+    P->dep_sorted = true;
     return 0;
 }
 

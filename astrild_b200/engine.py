@@ -113,6 +113,20 @@ class PkEngine:
             self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
             _lib.call("apk_plan_set_workspace", self._plan, _ptr(self._workspace), self._workspace.numel())
 
+    # ------------------------------------------------------------------ per-kernel timing
+    def enable_timing(self, on: bool = True) -> None:
+        _lib.call("apk_plan_enable_timing", self._plan, int(on))
+
+    def last_deposit_ms(self) -> dict:
+        ms = (ct.c_float * 4)()
+        _lib.call("apk_plan_last_deposit_ms", self._plan, ms)
+        return {"key": ms[0], "sort": ms[1], "bounds": ms[2], "deposit": ms[3]}
+
+    def last_bin_ms(self, binning: "Binning") -> dict:
+        ms = (ct.c_float * 2)()
+        _lib.call("apk_binning_last_ms", binning.handle, ms)
+        return {"bin": ms[0], "fold": ms[1]}
+
     # ------------------------------------------------------------------ stage 1: deposit
     def _positions(self, pos):
         """-> (p0, p1, p2, layout, dtype, np, keepalive) on this device."""

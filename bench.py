@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py -- P(k) pipeline throughput (deposit + r2c FFT + shell binning) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+
+One "step" = one complete P(k) of one synthetic particle set: deposit (sort + tiled deposit;
+twice when interlaced), r2c FFT(s), fused binning, result on the host.  Prints ONE JSON line.
+
+Workloads (BASELINE.json configs):
+  c3  1024^3 Zel'dovich particles, TSC + interlacing + window compensation, 1024^3 mesh  -- the
+      configuration the metric is quoted on; default when the device has the memory for it
+  c2  512^3 Zel'dovich particles, CIC, 512^3 mesh
+  c1  128^3 uniform particles, CIC, 128^3 mesh (the reference's CPU-runnable case)
+Inputs are far larger than L2 (126 MB), so no explicit L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c1": dict(n=128, mesh=128, box=1000.0, resampler="cic", interlaced=False, compensated=False, seed=12345,
+               kind="uniform", name="c1: 128^3 uniform particles, CIC, 128^3 mesh"),
+    "c2": dict(n=512, mesh=512, box=1000.0, resampler="cic", interlaced=False, compensated=False, seed=2024,
+               kind="zeldovich", name="c2: 512^3 Zel'dovich particles, CIC, 512^3 mesh"),
+    "c3": dict(n=1024, mesh=1024, box=1000.0, resampler="tsc", interlaced=True, compensated=True, seed=31337,
+               kind="zeldovich", name="c3: 1024^3 Zel'dovich particles, TSC + interlacing + compensation, 1024^3 mesh"),
+}
+METRIC = "P(k) pipeline Mparticles/s (deposit+FFT+binning)"
+UNIT = "Mparticles/s"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle restating pmesh/nbodykit) on host cores
+# ------------------------------------------------------------------------------------------
+def cpu_step(wl: dict, threads: int, sample_particles: int, sample_planes: int, state: dict) -> dict:
+    """One bounded sample of the CPU path, scaled to the full workload.  Returns seconds."""
+    from oracle import pk_oracle as o, pk_oracle_fast as f
+    import scipy.fft as sfft
+
+    n, N, L = wl["n"], wl["mesh"], wl["box"]
+    Np = n ** 3
+    ns = min(sample_particles, Np)
+    if "canvas" not in state:
+        state["canvas"] = np.zeros((N, N, N), dtype=np.float64)
+    if "pos" not in state:
+        state["pos"] = lattice_sample(wl, ns)
+    passes = 2 if wl["interlaced"] else 1
+    t0 = time.perf_counter()
+    for i in range(passes):
+        f.paint(state["pos"], None, N, L, wl["resampler"], 0.5 * i, out=state["canvas"])
+    t_dep = (time.perf_counter() - t0) * (Np / ns)
+    # FFT sample: the 3-D r2c is N planes of 2-D r2c over (y,z) + N*Nk pencils of 1-D c2c along x.
+    sp = min(sample_planes, N)
+    Nk = N // 2 + 1
+    t0 = time.perf_counter()
+    c = sfft.rfft2(state["canvas"][:sp], axes=(1, 2), workers=threads)
+    t_2d = (time.perf_counter() - t0) * (N / sp)
+    pencils = np.ascontiguousarray(np.broadcast_to(c[:1, :sp, :], (N, sp, Nk)))
+    t0 = time.perf_counter()
+    sfft.fft(pencils, axis=0, workers=threads, overwrite_x=True)
+    t_1d = (time.perf_counter() - t0) * (N / sp)
+    t_fft = (t_2d + t_1d) * passes
+    # binning sample: sp x-planes of the k-grid
+    t0 = time.perf_counter()
+    if wl["interlaced"]:
+        kx, ky, kz = o.k_tables(N, L)
+        ph = np.exp(0.5j * (kx[:sp, None, None] + ky[None, :, None] + kz[None, None, :]) * (L / N))
+        c = 0.5 * c + 0.5 * c * ph
+    if wl["compensated"]:
+        w = o.compensation_1d(wl["resampler"], wl["interlaced"], N)
+        c = c / (w[:sp, None, None] * w[None, :, None] * w[None, None, :Nk])
+    kxs, kys, kzs = o.k_tables(N, L)
+    edges = o.k_edges(N, L, 2 * np.pi / L)
+    e2 = edges ** 2
+    nb = len(edges) + 1
+    cc = np.ascontiguousarray(c)
+
+    def work(rng_):
+        xs, yr, yi = np.zeros(nb), np.zeros(nb), np.zeros(nb)
+        nsum = np.zeros(nb, dtype=np.int64)
+        f.lib().orc_bin_power(f._ptr(cc), None, N, f._ptr(kxs), f._ptr(kys), f._ptr(kzs), f._ptr(e2), len(edges),
+                              L ** 3, f._ptr(xs), f._ptr(yr), f._ptr(yi), f._ptr(nsum), int(rng_[0]), int(rng_[1]))
+        return nsum.sum()
+
+    b = np.linspace(0, sp, max(1, min(threads, sp)) + 1).astype(int)
+    if threads == 1:
+        work((0, sp))
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, zip(b[:-1], b[1:])))
+    t_bin = (time.perf_counter() - t0) * (N / sp)
+    return {"deposit": t_dep, "fft": t_fft, "bin": t_bin, "total": t_dep + t_fft + t_bin}
+
+
+def lattice_sample(wl: dict, ns: int) -> np.ndarray:
+    """First ns particles of a lattice-ordered set with rms 1-cell Gaussian displacements: the same
+    memory-access coherence as the Zel'dovich workload (uniform sets: uniform random)."""
+    n, L = wl["n"], wl["box"]
+    rng = np.random.default_rng(wl["seed"])
+    if wl["kind"] == "uniform":
+        return (rng.random((ns, 3)) * L).astype(np.float32)
+    idx = np.arange(ns, dtype=np.int64)
+    q = np.stack([idx // (n * n), (idx // n) % n, idx % n], axis=1).astype(np.float64)
+    pos = (q + 0.5 + rng.normal(0.0, 1.0, (ns, 3))) / n
+    return ((pos - np.floor(pos)) * L).astype(np.float32)
+
+
+def cpu_sample_desc(wl, sample_particles, sample_planes, threads):
+    return (f"deposit of the first {min(sample_particles, wl['n'] ** 3)} particles (lattice order) onto the full {wl['mesh']}^3 f64 mesh "
+            f"(1 thread, scaled to Np); {min(sample_planes, wl['mesh'])} of {wl['mesh']} planes of 2-D r2c + as many "
+            f"x-pencil blocks of 1-D c2c (scipy pocketfft f64, {threads} threads, scaled); binning of "
+            f"{min(sample_planes, wl['mesh'])} x-planes ({threads} threads, scaled)")
+
+
+def run_reference(args, wl_key: str) -> None:
+    """--impl reference: the reference's own CPU path.  nbodykit/pmesh/pfft are not installable
+    here (no MPI/FFTW, no network), so this times the oracle port that restates them."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pk_oracle_fast as f
+    f.build()
+    wl = WORKLOADS[wl_key]
+    threads = os.cpu_count() or 1
+    sp, spl = 1 << 22, 32
+    state: dict = {}
+    for _ in range(args.warmup):
+        cpu_step(wl, threads, sp, spl, state)
+    times = [cpu_step(wl, threads, sp, spl, state) for _ in range(args.steps)]
+    tot = sum(t["total"] for t in times)
+    Np = wl["n"] ** 3
+    value = Np * args.steps / tot / 1e6
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic",
+           "config": {"workload": wl["name"], "particles": Np, "mesh": wl["mesh"], "boxsize": wl["box"]},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                            "sample": cpu_sample_desc(wl, sp, spl, threads)},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "stages_s": {k: statistics.mean(t[k] for t in times) for k in ("deposit", "fft", "bin")}}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.path = gpu_index, None, f"/tmp/apk_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict | None:
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, wl_key: str) -> None:
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the P(k) path has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import astrild_b200 as ab
+    from astrild_b200 import synthetic
+
+    wl = WORKLOADS[wl_key]
+    n, N, L = wl["n"], wl["mesh"], wl["box"]
+    Np = n ** 3
+    kmin = 2 * np.pi / L
+
+    if world > 1:
+        from astrild_b200 import distributed
+        runner = distributed.SlabPk(N, L, resampler=wl["resampler"], interlaced=wl["interlaced"],
+                                    compensated=wl["compensated"], device=dev)
+        a, b = runner.lattice_planes(n)
+        pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev, x_planes=(a, b)) if wl["kind"] == "zeldovich" \
+            else tuple(c[rank::world].contiguous() for c in synthetic.uniform_particles(n, wl["seed"], dev))
+        torch.cuda.empty_cache()
+
+        def step():
+            return runner.power(pos, pos_scale=1.0, kmin=kmin, normalize=True)
+
+        def e2e_step(host_pos):
+            return runner.power(tuple(host_pos), pos_scale=1.0, kmin=kmin, normalize=True)
+        eng = runner.eng
+        binning = None
+    else:
+        if wl["kind"] == "zeldovich":
+            pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev)
+        else:
+            pos = synthetic.uniform_particles(n, wl["seed"], dev)
+        torch.cuda.empty_cache()
+        eng = ab.get_engine(N, L, dev)
+        comp = (wl["resampler"], wl["interlaced"]) if wl["compensated"] else None
+        binning = eng.binning(kmin=kmin, compensation=comp, interlaced=wl["interlaced"])
+        mesh1 = eng.new_mesh()
+        mesh2 = eng.new_mesh() if wl["interlaced"] else None
+        eng.ensure_workspace(Np, False)
+        scale = L ** 3 * (N ** 3 / Np) ** 2 / float(N) ** 6          # normalize=True, unit masses: W = Np
+        stage_ev = []
+
+        def step(record=None):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record is not None else None
+            if ev: ev[0].record()
+            eng.deposit(pos, None, wl["resampler"], 0.0, 1.0, "sorted", out=mesh1)
+            d1 = eng.last_deposit_ms() if record is not None else None
+            if mesh2 is not None:
+                eng.deposit(pos, None, wl["resampler"], 0.5, 1.0, "sorted", out=mesh2)
+                d2 = eng.last_deposit_ms() if record is not None else None
+            if ev: ev[1].record()
+            c1 = eng.r2c(mesh1)
+            c1s = eng.r2c(mesh2) if mesh2 is not None else None
+            if ev: ev[2].record()
+            raw = eng.bin_power_raw(binning, c1, c1s)
+            if ev: ev[3].record()
+            res = eng.finish(raw, binning, scale)                    # D2H of the shell sums: the result
+            if record is not None:
+                b = eng.last_bin_ms(binning)
+                rec = {"deposit_stage": ev[0].elapsed_time(ev[1]), "fft": ev[1].elapsed_time(ev[2]),
+                       "bin_stage": ev[2].elapsed_time(ev[3]), "bin_kernel": b["bin"], "bin_fold": b["fold"]}
+                for k in d1:
+                    rec["dep_" + k] = d1[k] + (d2[k] if mesh2 is not None else 0.0)
+                rec["dep_launches"] = 2 if mesh2 is not None else 1
+                record.append(rec)
+            return res
+
+        def e2e_step(host_pos):
+            mesh = ab.CatalogMesh(tuple(host_pos), L, N, resampler=wl["resampler"], interlaced=wl["interlaced"],
+                                  compensated=wl["compensated"], normalize=True, pos_scale=1.0, device=dev,
+                                  method="sorted")
+            r = ab.FFTPower(mesh, mode="1d", kmin=kmin)
+            return r.power
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput --------------------------------------------
+    eng.enable_timing(True)
+    for _ in range(args.warmup):
+        res = step()
+    sampler = ClockSampler(local_rank)
+    records: list = []
+    barrier()
+    sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for _ in range(args.steps):
+        res = step(records) if world == 1 else step()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = t_start.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = Np / (ms_per_step * 1e-3) / 1e6
+
+    # ---------------- end to end through the public API, host buffers ------------------------
+    host_pos = [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in pos]
+    for h, c in zip(host_pos, pos):
+        h.copy_(c)
+    h2d = sum(h.numel() * h.element_size() for h in host_pos)
+    cpu_sp, cpu_planes = 1 << 23, 64
+    cpu_pos = None
+    if world == 1 and not args.no_cpu_baseline:      # the CPU baseline times a prefix of the SAME particles
+        cpu_pos = (torch.stack([c[:cpu_sp] for c in pos], dim=1).double() * L).float().cpu().numpy()
+    if world == 1:
+        del pos
+        torch.cuda.empty_cache()
+    e2e_steps = max(1, min(args.steps, 5))
+    e2e_step(host_pos)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pw = e2e_step(host_pos)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    nb1 = len(res["edges"]) + 1
+    d2h = 4 * nb1 * 8 + 16
+    e2e = {"value": Np / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world) if world > 1 else int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+           "api": "astrild_b200.CatalogMesh(host x,y,z pinned) -> FFTPower(mode='1d', kmin=2pi/L)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant hand-written kernel ---------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    roofline, stages = None, None
+    n_meshes = 2 if wl["interlaced"] else 1
+    if records:
+        avg = {k: statistics.mean(r[k] for r in records) for k in records[0]}
+        dep_bytes = Np * 12 + 4 * N ** 3                               # per deposit launch
+        bin_bytes = 8 * N * N * (N // 2 + 1) * n_meshes
+        fft_bytes = (4 * N ** 3 + 8 * N * N * (N // 2 + 1)) * n_meshes
+        dep_kernel_ms = avg["dep_deposit"] / n_meshes
+        cand = {
+            "brick_deposit_kernel": (dep_bytes, dep_kernel_ms),
+            "bin_power_kernel": (bin_bytes, avg["bin_kernel"]),
+        }
+        name = max(cand, key=lambda k: cand[k][1] * (n_meshes if k == "brick_deposit_kernel" else 1))
+        by, t = cand[name]
+        roofline = {"bound": "hbm", "kernel": name, "achieved": by / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                    "frac": by / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": by, "ms_per_launch": t}
+        stages = {
+            "ms": {k: round(v, 4) for k, v in avg.items() if k != "dep_launches"},
+            "deposit_stage_GBps": n_meshes * dep_bytes / (avg["deposit_stage"] * 1e-3) / 1e9,
+            "fft_GBps_algorithmic": fft_bytes / (avg["fft"] * 1e-3) / 1e9,
+            "bin_kernel_GBps": bin_bytes / (avg["bin_kernel"] * 1e-3) / 1e9,
+            "bin_kernel_frac": bin_bytes / (avg["bin_kernel"] * 1e-3) / 1e9 / peak,
+            "brick_deposit_GBps": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9,
+            "brick_deposit_frac": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9 / peak,
+        }
+
+    # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import pk_oracle_fast as f
+        f.build()
+        t = cpu_step(wl, 1, cpu_sp, cpu_planes, {"pos": cpu_pos})
+        cpu = {"value": Np / t["total"] / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": cpu_sample_desc(wl, cpu_sp, cpu_planes, 1), "seconds_scaled": {k: round(v, 2) for k, v in t.items()}}
+
+    kernels_per_step = (3 * n_meshes + 2) if world == 1 else None
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32 mesh/FFT, f64 index + shell sums", "data": "synthetic",
+           "config": {"workload": wl["name"], "particles": Np, "mesh": N, "boxsize": L, "resampler": wl["resampler"],
+                      "interlaced": wl["interlaced"], "compensated": wl["compensated"],
+                      "parallelism": "single GPU" if world == 1 else f"x-slab decomposition over {world} GPUs",
+                      "l2": "inputs >> L2 (126 MB): no flush needed"},
+           "clocks": clocks, "e2e": e2e,
+           "gpu_launches": (kernels_per_step * args.steps) if kernels_per_step else None,
+           "gpu_launches_note": "hand-written kernels per step: key + bounds + brick deposit per mesh, bin + fold; "
+                                "CUB radix sort and cuFFT launches are library kernels and not counted",
+           "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+           "check": {"first_bins_P": [float(x) for x in res["power"].real[:3]], "modes0": int(res["modes"][0])}}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def pick_workload(args) -> str:
+    if args.workload:
+        return args.workload
+    if args.impl == "reference":
+        return os.environ.get("APK_BENCH_WORKLOAD", "c3")
+    try:
+        import torch
+        if torch.cuda.is_available():
+            free, total = torch.cuda.mem_get_info(int(os.environ.get("LOCAL_RANK", "0")))
+            world = int(os.environ.get("WORLD_SIZE", "1"))
+            return "c3" if free * world > 110e9 else "c2"
+    except Exception:
+        pass
+    return "c3"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = pick_workload(args)
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

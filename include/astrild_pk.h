@@ -62,6 +62,15 @@ int apk_plan_set_workspace(apk_plan *plan, void *workspace, size_t bytes);
  * sent to and added by the ring neighbours); single-GPU plans report 0, 0.                    */
 int apk_plan_ghost_planes(const apk_plan *plan, int *n_lo, int *n_hi);
 
+/* ---- per-kernel timing (CUDA events recorded inside the library, on the caller's stream) ---- */
+/* on != 0: apk_deposit / apk_bin_power bracket their kernels with events.                     */
+int apk_plan_enable_timing(apk_plan *plan, int on);
+/* last apk_deposit on this plan, ms: [0] key kernel, [1] radix sort (CUB), [2] brick bounds,
+ * [3] brick deposit kernel (sorted path) or the atomic kernel.  Synchronises on the last event. */
+int apk_plan_last_deposit_ms(apk_plan *plan, float ms[4]);
+/* last apk_bin_power on this binning, ms: [0] fused binning kernel, [1] fold of per-CTA copies  */
+int apk_binning_last_ms(apk_binning *binning, float ms[2]);
+
 /* ---- deposit (pm.paint) ------------------------------------------------------------------- */
 /* Adds mass * W(cell - g) to `mesh` for every particle, g = pos * pos_scale * N + shift (grid
  * units; cell i is centred on g = i), periodic.  pos_scale = 1/L for positions in box-length
