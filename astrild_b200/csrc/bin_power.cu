@@ -237,24 +237,35 @@ bin_power_kernel(BinArgs A) {
     }
 }
 
-// fold the per-CTA copies in a fixed order (deterministic given the copies)
-__global__ void bin_fold_kernel(const double *part_k, const double *part_p, const double *part_pim,
-                                const unsigned long long *part_n, int ctas, int nb1, double *ksum,
-                                double *psum_re, double *psum_im, long long *nmodes) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// fold the per-CTA copies in a fixed order (deterministic given the copies): one warp per bin
+__global__ void __launch_bounds__(128)
+bin_fold_kernel(const double *part_k, const double *part_p, const double *part_pim,
+                const unsigned long long *part_n, int ctas, int nb1, double *ksum,
+                double *psum_re, double *psum_im, long long *nmodes) {
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (b >= nb1) return;
     double k = 0.0, p = 0.0, q = 0.0;
     unsigned long long n = 0;
-    for (int c = 0; c < ctas; ++c) {
+    for (int c = lane; c < ctas; c += 32) {
         k += part_k[(size_t)c * nb1 + b];
         p += part_p[(size_t)c * nb1 + b];
         q += part_pim[(size_t)c * nb1 + b];
         n += part_n[(size_t)c * nb1 + b];
     }
-    ksum[b] = k;
-    psum_re[b] = p;
-    psum_im[b] = q;
-    nmodes[b] = (long long)n;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k += __shfl_xor_sync(0xffffffffu, k, o);
+        p += __shfl_xor_sync(0xffffffffu, p, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+    }
+    if (lane == 0) {
+        ksum[b] = k;
+        psum_re[b] = p;
+        psum_im[b] = q;
+        nmodes[b] = (long long)n;
+    }
 }
 
 size_t bin_smem_bytes(int nedges) {
@@ -321,7 +332,7 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
     }
     if (rc) return rc;
     if (timing) APK_CUDA(cudaEventRecord(B->ev[1], st));
-    bin_fold_kernel<<<(nb1 + 127) / 128, 128, 0, st>>>(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1,
+    bin_fold_kernel<<<(nb1 + 3) / 4, 128, 0, st>>>(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1,
                                                       ksum, psum_re, psum_im, (long long *)nmodes);
     APK_CUDA(cudaGetLastError());
     if (timing) APK_CUDA(cudaEventRecord(B->ev[2], st));

@@ -8,11 +8,16 @@
 // traffic is real but not credited.
 //
 // Pipeline (all on one stream, no host sync):
-//   1. brick_key_kernel     every particle -> key of the 12x12x32-cell brick that holds its HOME
-//                           cell (float64 index arithmetic, identical to the oracle's), payload =
-//                           brick-local coordinates as 3 floats (+ mass).
-//   2. cub::DeviceRadixSort on the brick key (only the bits in use), payload moves with it.
-//   3. brick_bounds_kernel  lower_bound per brick in the sorted keys.
+//   1. brick_count_kernel   every particle -> key of the 12x12x32-cell brick that holds its HOME
+//                           cell (float64 index arithmetic, identical to the oracle's); per-brick
+//                           counts with warp-aggregated RED (__match_any_sync: one atomic per run
+//                           of equal keys in a warp -- snapshot order is spatially coherent).
+//   2. brick_scan_kernel    exclusive scan of the counts -> brick_start[], cursors.
+//   3. brick_scatter_kernel keys are recomputed (never stored); each run of equal keys claims
+//                           its slots with ONE atomicAdd on the brick's cursor and writes its
+//                           payload = brick-local coordinates as 3 floats (+ mass), contiguously.
+//                           One read and one write of the particles replace a multi-pass radix
+//                           sort; order inside a brick is arbitrary (the deposit does not care).
 //   4. brick_deposit_kernel persistent CTAs pull bricks from a counter; per brick and per chunk
 //      of <= CH particles: counting-sort the chunk by home cell inside shared memory (native
 //      32-bit ATOMS.ADD gives each particle its rank), then one thread per home cell sums the
@@ -25,7 +30,6 @@
 //      zeros; bricks are visited x-major so neighbouring tiles meet in L2.
 #include "apk_common.cuh"
 #include "deposit_common.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <type_traits>
 
@@ -43,7 +47,6 @@ struct P4 { float x, y, z, m; };
 struct BrickGrid {
     int nbx, nby, nbz;   // bricks per axis (x counts local planes for slab plans)
     int nbricks;
-    int bits;            // key bits in use
 };
 
 static BrickGrid make_brick_grid(const DepositGeom &G) {
@@ -52,8 +55,6 @@ static BrickGrid make_brick_grid(const DepositGeom &G) {
     B.nby = (G.N + BY - 1) / BY;
     B.nbz = (G.N + BZ - 1) / BZ;
     B.nbricks = B.nbx * B.nby * B.nbz;
-    B.bits = 1;
-    while ((1u << B.bits) < (unsigned)B.nbricks && B.bits < 32) ++B.bits;
     return B;
 }
 
@@ -61,47 +62,121 @@ static BrickGrid make_brick_grid(const DepositGeom &G) {
 template <int S>
 __device__ __forceinline__ double home_of(double g) { return (S == 2) ? floor(g) : floor(g + 0.5); }
 
-template <int S, typename PT, bool SOA, bool MASS, typename VT>
-__global__ void __launch_bounds__(256)
-brick_key_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
-                 const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, BrickGrid B,
-                 unsigned int *__restrict__ keys, VT *__restrict__ vals) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
-        double g[3];
-        if (SOA) { g[0] = (double)p0[p]; g[1] = (double)p1[p]; g[2] = (double)p2[p]; }
-        else     { g[0] = (double)p0[3 * p]; g[1] = (double)p0[3 * p + 1]; g[2] = (double)p0[3 * p + 2]; }
-        int b[3];
-        float l[3];
+// brick key and brick-local coordinates of particle p (shared by the count and scatter passes so
+// both see bit-identical keys)
+template <int S, typename PT, bool SOA>
+__device__ __forceinline__ unsigned int brick_of(const PT *__restrict__ p0, const PT *__restrict__ p1,
+                                                 const PT *__restrict__ p2, long long p, const DepositGeom &G,
+                                                 const BrickGrid &B, float (&l)[3]) {
+    double g[3];
+    if (SOA) { g[0] = (double)p0[p]; g[1] = (double)p1[p]; g[2] = (double)p2[p]; }
+    else     { g[0] = (double)p0[3 * p]; g[1] = (double)p0[3 * p + 1]; g[2] = (double)p0[3 * p + 2]; }
+    int b[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            g[d] = g[d] * G.scale + G.shift;
-            const double h = home_of<S>(g[d]);
-            const double frac = g[d] - h;                       // [0,1) CIC, [-0.5,0.5) TSC
-            int hl = (d == 0) ? G.local_plane((long long)h) : wrap_index((long long)h, G.N);
-            if (hl < 0) hl = 0;                                 // slab plan, particle not routed here: caller error
-            const int edge = d == 0 ? BX : (d == 1 ? BY : BZ);
-            b[d] = hl / edge;
-            l[d] = (float)(frac + (double)(hl - b[d] * edge));
+    for (int d = 0; d < 3; ++d) {
+        g[d] = g[d] * G.scale + G.shift;
+        const double h = home_of<S>(g[d]);
+        const double frac = g[d] - h;                       // [0,1) CIC, [-0.5,0.5) TSC
+        int hl = (d == 0) ? G.local_plane((long long)h) : wrap_index((long long)h, G.N);
+        if (hl < 0) hl = 0;                                 // slab plan, particle not routed here: caller error
+        const int edge = d == 0 ? BX : (d == 1 ? BY : BZ);
+        b[d] = hl / edge;
+        l[d] = (float)(frac + (double)(hl - b[d] * edge));
+    }
+    return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
+}
+
+constexpr int PART_THREADS = 256;
+constexpr int PART_ITEMS = 4;    // particles per thread per tile (ILP on the loads)
+
+template <int S, typename PT, bool SOA>
+__global__ void __launch_bounds__(PART_THREADS)
+brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2, long long np,
+                   DepositGeom G, BrickGrid B, unsigned int *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const long long tile = (long long)PART_THREADS * PART_ITEMS;
+    for (long long base = (long long)blockIdx.x * tile; base < np; base += (long long)gridDim.x * tile) {
+        unsigned int key[PART_ITEMS];
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            const long long p = base + k * PART_THREADS + threadIdx.x;
+            float l[3];
+            key[k] = p < np ? brick_of<S, PT, SOA>(p0, p1, p2, p, G, B, l) : 0xffffffffu;
         }
-        keys[p] = (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
-        VT v;
-        v.x = l[0]; v.y = l[1]; v.z = l[2];
-        if constexpr (MASS) v.m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
-        vals[p] = v;
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            const unsigned int peers = __match_any_sync(0xffffffffu, key[k]);
+            if (key[k] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(counts + key[k], (unsigned int)__popc(peers));
+        }
     }
 }
 
-__global__ void brick_bounds_kernel(const unsigned int *__restrict__ keys, long long np, int nbricks,
-                                    unsigned int *__restrict__ start) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > nbricks) return;
-    long long lo = 0, hi = np;   // lower_bound(keys, b)
-    while (lo < hi) {
-        const long long mid = (lo + hi) >> 1;
-        if (keys[mid] < (unsigned)b) lo = mid + 1; else hi = mid;
+// exclusive scan of counts[0..n) -> start[0..n], cursor[0..n) = start; one CTA (n is ~10^4..10^6)
+__global__ void __launch_bounds__(1024)
+brick_scan_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *__restrict__ start,
+                  unsigned int *__restrict__ cursor) {
+    __shared__ unsigned int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int a = min(tid * per, n), b = min(a + per, n);
+    unsigned int s = 0;
+    for (int i = a; i < b; ++i) s += counts[i];
+    unsigned int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    start[b] = (unsigned int)lo;
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const unsigned int w = wsum[lane];
+        unsigned int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        wsum[lane] = wi - w;
+    }
+    __syncthreads();
+    unsigned int run = wsum[warp] + incl - s;
+    for (int i = a; i < b; ++i) { start[i] = run; cursor[i] = run; run += counts[i]; }
+    if (tid == 1023) start[n] = run;
+}
+
+template <int S, typename PT, bool SOA, bool MASS, typename VT>
+__global__ void __launch_bounds__(PART_THREADS)
+brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
+                     const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, BrickGrid B,
+                     unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const long long tile = (long long)PART_THREADS * PART_ITEMS;
+    for (long long base = (long long)blockIdx.x * tile; base < np; base += (long long)gridDim.x * tile) {
+        unsigned int key[PART_ITEMS];
+        VT v[PART_ITEMS];
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            const long long p = base + k * PART_THREADS + threadIdx.x;
+            key[k] = 0xffffffffu;
+            if (p < np) {
+                float l[3];
+                key[k] = brick_of<S, PT, SOA>(p0, p1, p2, p, G, B, l);
+                v[k].x = l[0]; v[k].y = l[1]; v[k].z = l[2];
+                if constexpr (MASS) v[k].m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PART_ITEMS; ++k) {
+            const unsigned int peers = __match_any_sync(0xffffffffu, key[k]);
+            const int leader = __ffs(peers) - 1;
+            unsigned int slot = 0;
+            if (key[k] != 0xffffffffu && lane == leader) slot = atomicAdd(cursor + key[k], (unsigned int)__popc(peers));
+            slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & lt_mask);
+            if (key[k] != 0xffffffffu) vals[slot] = v[k];
+        }
+    }
 }
 
 template <int S>
@@ -311,20 +386,15 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     }
 }
 
+static size_t max_bricks(const apk_plan *P) {
+    return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + BZ - 1) / BZ);
+}
+static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
 size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass) {
     if (np <= 0) return 0;
     const size_t vs = with_mass ? sizeof(P4) : sizeof(P3);
-    size_t cub_bytes = 0;
-    // size query only (no kernel launch)
-    if (with_mass)
-        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned int *)nullptr, (unsigned int *)nullptr,
-                                        (const P4 *)nullptr, (P4 *)nullptr, np, 0, 32);
-    else
-        cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned int *)nullptr, (unsigned int *)nullptr,
-                                        (const P3 *)nullptr, (P3 *)nullptr, np, 0, 32);
-    const size_t nbricks_max = (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + BZ - 1) / BZ);
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    return al(4 * (size_t)np) * 2 + al(vs * (size_t)np) * 2 + al(4 * (nbricks_max + 2)) + 256 + al(cub_bytes);
+    return align256(vs * (size_t)np) + 3 * align256(4 * (max_bricks(P) + 2)) + 256;
 }
 
 template <int S, typename PT, bool SOA, bool MASS>
@@ -332,33 +402,31 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
                       int mass_dtype, long long np, const DepositGeom &G, float *mesh, cudaStream_t st) {
     using VT = typename std::conditional<MASS, P4, P3>::type;
     const BrickGrid B = make_brick_grid(G);
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t need = deposit_sorted_workspace_bytes(P, np, MASS);
     APK_REQUIRE(P->workspace && P->workspace_bytes >= need,
                 "apk_deposit: sorted path needs %zu workspace bytes, %zu set (apk_plan_workspace_bytes / apk_plan_set_workspace)",
                 need, P->workspace_bytes);
     APK_REQUIRE(np < 0xffffffffLL, "apk_deposit: more than 2^32-1 particles on one device");
     unsigned char *w = (unsigned char *)P->workspace;
-    unsigned int *keys_a = (unsigned int *)w; w += al(4 * (size_t)np);
-    unsigned int *keys_b = (unsigned int *)w; w += al(4 * (size_t)np);
-    VT *vals_a = (VT *)w; w += al(sizeof(VT) * (size_t)np);
-    VT *vals_b = (VT *)w; w += al(sizeof(VT) * (size_t)np);
-    const size_t nbricks_max = (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + BZ - 1) / BZ);
-    unsigned int *brick_start = (unsigned int *)w; w += al(4 * (nbricks_max + 2));
-    unsigned int *counter = (unsigned int *)w; w += 256;
-    void *cub_tmp = w;
-    size_t cub_bytes = P->workspace_bytes - (size_t)(w - (unsigned char *)P->workspace);
+    VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np);
+    const size_t tab = align256(4 * (max_bricks(P) + 2));
+    unsigned int *counts = (unsigned int *)w; w += tab;
+    unsigned int *brick_start = (unsigned int *)w; w += tab;
+    unsigned int *cursor = (unsigned int *)w; w += tab;
+    unsigned int *counter = (unsigned int *)w;
 
-    const int kb = (int)std::min<long long>((np + 255) / 256, (long long)P->num_sms * 16);
+    const long long tile = (long long)PART_THREADS * PART_ITEMS;
+    const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)P->num_sms * 8);
     P->mark(0, st);
-    brick_key_kernel<S, PT, SOA, MASS, VT><<<kb, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass,
-                                                              mass_dtype == APK_F64, np, G, B, keys_a, vals_a);
+    APK_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)(B.nbricks + 1), st));
+    brick_count_kernel<S, PT, SOA><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
     APK_CUDA(cudaGetLastError());
     P->mark(1, st);
-    APK_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const unsigned int *)keys_a, keys_b,
-                                             (const VT *)vals_a, vals_b, np, 0, B.bits, st));
+    brick_scan_kernel<<<1, 1024, 0, st>>>(counts, B.nbricks, brick_start, cursor);
+    APK_CUDA(cudaGetLastError());
     P->mark(2, st);
-    brick_bounds_kernel<<<(B.nbricks + 1 + 255) / 256, 256, 0, st>>>(keys_b, np, B.nbricks, brick_start);
+    brick_scatter_kernel<S, PT, SOA, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
+        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
     APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
 
@@ -370,7 +438,7 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     if (per_sm < 1) per_sm = 1;
     const int ctas = std::min(P->num_sms * per_sm, B.nbricks);
     P->mark(3, st);
-    kern<<<ctas, DEP_THREADS, smem, st>>>(vals_b, brick_start, G, B, counter, mesh);
+    kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, G, B, counter, mesh);
     APK_CUDA(cudaGetLastError());
     P->mark(4, st);
     P->dep_timed = P->timing;

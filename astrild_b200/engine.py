@@ -120,7 +120,7 @@ class PkEngine:
     def last_deposit_ms(self) -> dict:
         ms = (ct.c_float * 4)()
         _lib.call("apk_plan_last_deposit_ms", self._plan, ms)
-        return {"key": ms[0], "sort": ms[1], "bounds": ms[2], "deposit": ms[3]}
+        return {"count": ms[0], "scan": ms[1], "scatter": ms[2], "deposit": ms[3]}
 
     def last_bin_ms(self, binning: "Binning") -> dict:
         ms = (ct.c_float * 2)()

@@ -65,7 +65,7 @@ int apk_plan_ghost_planes(const apk_plan *plan, int *n_lo, int *n_hi);
 /* ---- per-kernel timing (CUDA events recorded inside the library, on the caller's stream) ---- */
 /* on != 0: apk_deposit / apk_bin_power bracket their kernels with events.                     */
 int apk_plan_enable_timing(apk_plan *plan, int on);
-/* last apk_deposit on this plan, ms: [0] key kernel, [1] radix sort (CUB), [2] brick bounds,
+/* last apk_deposit on this plan, ms: [0] brick count kernel, [1] brick scan, [2] brick scatter,
  * [3] brick deposit kernel (sorted path) or the atomic kernel.  Synchronises on the last event. */
 int apk_plan_last_deposit_ms(apk_plan *plan, float ms[4]);
 /* last apk_bin_power on this binning, ms: [0] fused binning kernel, [1] fold of per-CTA copies  */

@@ -95,7 +95,7 @@ def test_deposit_empty_and_clustered(ab, oracle_fast):
         want = oracle_fast.paint(pos, None, N, L, rs)
         for method in ("atomic", "sorted"):
             got = pm.paint(pos, resampler=rs, method=method).value
-            np.testing.assert_allclose(got, want, rtol=0, atol=3e-6 * want.max())
+            np.testing.assert_allclose(got, want, rtol=0, atol=2e-5 * want.max())  # 40000 fp32 adds into one cell
 
 
 # ------------------------------------------------------------------------------ binning
