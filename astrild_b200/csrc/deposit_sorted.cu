@@ -31,6 +31,7 @@
 #include "apk_common.cuh"
 #include "deposit_common.cuh"
 #include <algorithm>
+#include <cstdint>
 #include <type_traits>
 
 namespace apk {
@@ -62,51 +63,133 @@ static BrickGrid make_brick_grid(const DepositGeom &G) {
 template <int S>
 __device__ __forceinline__ double home_of(double g) { return (S == 2) ? floor(g) : floor(g + 0.5); }
 
+// floor(g) as double and as int32 without 64-bit conversion instructions (quarter-rate pipe):
+// adding 1.5*2^52 leaves rint(g) in the low word.  Valid for |g| < 2^31 grid units.
+__device__ __forceinline__ double floor_magic(double g, int &i) {
+    const double magic = 6755399441055744.0;
+    const double t = g + magic;
+    int r = __double2loint(t);
+    double rd = t - magic;
+    if (rd > g) { rd -= 1.0; r -= 1; }
+    i = r;
+    return rd;
+}
+
+__device__ __forceinline__ int wrap_index32(int i, int N) {
+    if ((unsigned)i < (unsigned)N) return i;
+    if (i < 0 && i >= -N) return i + N;
+    if (i >= N && i < 2 * N) return i - N;
+    const int r = i % N;
+    return r < 0 ? r + N : r;
+}
+
 // brick key and brick-local coordinates of particle p (shared by the count and scatter passes so
-// both see bit-identical keys)
-template <int S, typename PT, bool SOA>
-__device__ __forceinline__ unsigned int brick_of(const PT *__restrict__ p0, const PT *__restrict__ p1,
-                                                 const PT *__restrict__ p2, long long p, const DepositGeom &G,
+// both see bit-identical keys).  g = x * scale + shift in float64, exactly the oracle's expression.
+template <int S>
+__device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const DepositGeom &G,
                                                  const BrickGrid &B, float (&l)[3]) {
-    double g[3];
-    if (SOA) { g[0] = (double)p0[p]; g[1] = (double)p1[p]; g[2] = (double)p2[p]; }
-    else     { g[0] = (double)p0[3 * p]; g[1] = (double)p0[3 * p + 1]; g[2] = (double)p0[3 * p + 2]; }
     int b[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        g[d] = g[d] * G.scale + G.shift;
-        const double h = home_of<S>(g[d]);
-        const double frac = g[d] - h;                       // [0,1) CIC, [-0.5,0.5) TSC
-        int hl = (d == 0) ? G.local_plane((long long)h) : wrap_index((long long)h, G.N);
-        if (hl < 0) hl = 0;                                 // slab plan, particle not routed here: caller error
+        const double g = x[d] * G.scale + G.shift;
+        int hi;
+        const double h = floor_magic(S == 2 ? g : g + 0.5, hi);         // home cell
+        const float frac = (float)(g - h);                              // [0,1) CIC, [-0.5,0.5) TSC
+        int hl = wrap_index32(hi, G.N);
+        if (d == 0 && G.slab) {
+            hl -= G.plane0;
+            if (hl < 0) hl += G.N; else if (hl >= G.N) hl -= G.N;
+            if (hl >= G.nplanes) hl = 0;                                // not routed here: caller error
+        }
         const int edge = d == 0 ? BX : (d == 1 ? BY : BZ);
         b[d] = hl / edge;
-        l[d] = (float)(frac + (double)(hl - b[d] * edge));
+        l[d] = frac + (float)(hl - b[d] * edge);
     }
     return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
 }
 
-constexpr int PART_THREADS = 256;
-constexpr int PART_ITEMS = 4;    // particles per thread per tile (ILP on the loads)
+// coordinates of the 4 consecutive particles p4 .. p4+3 (clamped to np-1), all loads issued up
+// front; VEC: 128-bit loads (float columns / float AoS, 16-byte aligned bases)
+template <typename PT, bool SOA, bool VEC>
+__device__ __forceinline__ void load4(const PT *__restrict__ p0, const PT *__restrict__ p1,
+                                      const PT *__restrict__ p2, long long p4, long long np, double (&x)[4][3]) {
+    if constexpr (VEC) {
+        if (p4 + 3 < np) {
+            if (SOA) {
+                const float4 a = __ldcs(reinterpret_cast<const float4 *>(p0 + p4));
+                const float4 b = __ldcs(reinterpret_cast<const float4 *>(p1 + p4));
+                const float4 c = __ldcs(reinterpret_cast<const float4 *>(p2 + p4));
+                x[0][0] = a.x; x[1][0] = a.y; x[2][0] = a.z; x[3][0] = a.w;
+                x[0][1] = b.x; x[1][1] = b.y; x[2][1] = b.z; x[3][1] = b.w;
+                x[0][2] = c.x; x[1][2] = c.y; x[2][2] = c.z; x[3][2] = c.w;
+            } else {
+                const float4 a = __ldcs(reinterpret_cast<const float4 *>(p0 + 3 * p4));
+                const float4 b = __ldcs(reinterpret_cast<const float4 *>(p0 + 3 * p4 + 4));
+                const float4 c = __ldcs(reinterpret_cast<const float4 *>(p0 + 3 * p4 + 8));
+                x[0][0] = a.x; x[0][1] = a.y; x[0][2] = a.z; x[1][0] = a.w;
+                x[1][1] = b.x; x[1][2] = b.y; x[2][0] = b.z; x[2][1] = b.w;
+                x[2][2] = c.x; x[3][0] = c.y; x[3][1] = c.z; x[3][2] = c.w;
+            }
+            return;
+        }
+    }
+    PT t[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long p = min(p4 + k, np - 1);
+        if (SOA) { t[k][0] = p0[p]; t[k][1] = p1[p]; t[k][2] = p2[p]; }
+        else     { t[k][0] = p0[3 * p]; t[k][1] = p0[3 * p + 1]; t[k][2] = p0[3 * p + 2]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[k][d] = (double)t[k][d];
+}
 
-template <int S, typename PT, bool SOA>
+// run-length aggregation inside a warp: lanes holding the same key as their left neighbour form a
+// run; returns the run's head lane and this lane's offset in it (keys of a snapshot are coherent,
+// so runs are long; for random keys every lane is its own run)
+__device__ __forceinline__ void warp_runs(unsigned int key, int lane, int &head, int &offset, int &length) {
+    const unsigned int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned int heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    const unsigned int below = heads & ((2u << lane) - 1u);          // heads at or below this lane
+    head = 31 - __clz(below);
+    offset = lane - head;
+    const unsigned int above = heads & ~((2u << lane) - 1u);          // heads above this lane
+    const int next = above ? __ffs(above) - 1 : 32;
+    length = next - head;
+}
+
+constexpr int PART_THREADS = 256;
+constexpr int PART_ITEMS = 4;    // consecutive particles per thread per tile
+
+template <int S, typename PT, bool SOA, bool VEC>
 __global__ void __launch_bounds__(PART_THREADS)
 brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2, long long np,
                    DepositGeom G, BrickGrid B, unsigned int *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     for (long long base = (long long)blockIdx.x * tile; base < np; base += (long long)gridDim.x * tile) {
-        unsigned int key[PART_ITEMS];
+        const long long p4 = base + 4 * threadIdx.x;
+        double x[4][3];
+        load4<PT, SOA, VEC>(p0, p1, p2, p4, np, x);
+        unsigned int key[4];
 #pragma unroll
-        for (int k = 0; k < PART_ITEMS; ++k) {
-            const long long p = base + k * PART_THREADS + threadIdx.x;
+        for (int k = 0; k < 4; ++k) {
             float l[3];
-            key[k] = p < np ? brick_of<S, PT, SOA>(p0, p1, p2, p, G, B, l) : 0xffffffffu;
+            key[k] = brick_of<S>(x[k], G, B, l);
+            if (p4 + k >= np) key[k] = 0xffffffffu;
         }
+        int head, offset, length;
+        if (__all_sync(0xffffffffu, key[0] == key[1] && key[0] == key[2] && key[0] == key[3] && key[0] != 0xffffffffu)) {
+            warp_runs(key[0], lane, head, offset, length);      // the usual case: one run per thread
+            if (offset == 0) atomicAdd(counts + key[0], 4u * (unsigned int)length);
+        } else {
 #pragma unroll
-        for (int k = 0; k < PART_ITEMS; ++k) {
-            const unsigned int peers = __match_any_sync(0xffffffffu, key[k]);
-            if (key[k] != 0xffffffffu && lane == __ffs(peers) - 1) atomicAdd(counts + key[k], (unsigned int)__popc(peers));
+            for (int k = 0; k < 4; ++k) {
+                warp_runs(key[k], lane, head, offset, length);
+                if (key[k] != 0xffffffffu && offset == 0) atomicAdd(counts + key[k], (unsigned int)length);
+            }
         }
     }
 }
@@ -145,36 +228,47 @@ brick_scan_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *
     if (tid == 1023) start[n] = run;
 }
 
-template <int S, typename PT, bool SOA, bool MASS, typename VT>
+template <int S, typename PT, bool SOA, bool VEC, bool MASS, typename VT>
 __global__ void __launch_bounds__(PART_THREADS)
 brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
                      const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, BrickGrid B,
                      unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
     const int lane = threadIdx.x & 31;
-    const unsigned int lt_mask = (1u << lane) - 1u;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     for (long long base = (long long)blockIdx.x * tile; base < np; base += (long long)gridDim.x * tile) {
-        unsigned int key[PART_ITEMS];
-        VT v[PART_ITEMS];
+        const long long p4 = base + 4 * threadIdx.x;
+        double x[4][3];
+        load4<PT, SOA, VEC>(p0, p1, p2, p4, np, x);
+        unsigned int key[4];
+        VT v[4];
 #pragma unroll
-        for (int k = 0; k < PART_ITEMS; ++k) {
-            const long long p = base + k * PART_THREADS + threadIdx.x;
-            key[k] = 0xffffffffu;
-            if (p < np) {
-                float l[3];
-                key[k] = brick_of<S, PT, SOA>(p0, p1, p2, p, G, B, l);
-                v[k].x = l[0]; v[k].y = l[1]; v[k].z = l[2];
-                if constexpr (MASS) v[k].m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
+        for (int k = 0; k < 4; ++k) {
+            float l[3];
+            key[k] = brick_of<S>(x[k], G, B, l);
+            v[k].x = l[0]; v[k].y = l[1]; v[k].z = l[2];
+            if (p4 + k >= np) key[k] = 0xffffffffu;
+            if constexpr (MASS) {
+                const long long p = min(p4 + k, np - 1);
+                v[k].m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
             }
         }
-#pragma unroll
-        for (int k = 0; k < PART_ITEMS; ++k) {
-            const unsigned int peers = __match_any_sync(0xffffffffu, key[k]);
-            const int leader = __ffs(peers) - 1;
+        int head, offset, length;
+        if (__all_sync(0xffffffffu, key[0] == key[1] && key[0] == key[2] && key[0] == key[3] && key[0] != 0xffffffffu)) {
+            warp_runs(key[0], lane, head, offset, length);
             unsigned int slot = 0;
-            if (key[k] != 0xffffffffu && lane == leader) slot = atomicAdd(cursor + key[k], (unsigned int)__popc(peers));
-            slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & lt_mask);
-            if (key[k] != 0xffffffffu) vals[slot] = v[k];
+            if (offset == 0) slot = atomicAdd(cursor + key[0], 4u * (unsigned int)length);
+            slot = __shfl_sync(0xffffffffu, slot, head) + 4u * offset;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) vals[slot + k] = v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                warp_runs(key[k], lane, head, offset, length);
+                unsigned int slot = 0;
+                if (key[k] != 0xffffffffu && offset == 0) slot = atomicAdd(cursor + key[k], (unsigned int)length);
+                slot = __shfl_sync(0xffffffffu, slot, head) + offset;
+                if (key[k] != 0xffffffffu) vals[slot] = v[k];
+            }
         }
     }
 }
@@ -194,6 +288,66 @@ struct DepSmem {
                                     sizeof(float) * CH * (MASS ? 4 : 3) + 64;
 };
 
+__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// Window moments of the particles [beg, end) of one home cell, accumulated with packed FFMA2.
+// Layout: A[a][c] = float2 over the b-pair (first, last) of the window, Bm[a][c] = middle b (TSC only).
+template <int S, bool MASS>
+struct Moments {
+    float2 A[S][S];
+    float Bm[S][S];   // unused for S == 2
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int a = 0; a < S; ++a)
+#pragma unroll
+            for (int c = 0; c < S; ++c) { A[a][c] = make_float2(0.f, 0.f); Bm[a][c] = 0.f; }
+    }
+
+    __device__ __forceinline__ void add(float dx, float dy, float dz, float m) {
+        float wx[S], wz[S];
+        float2 wyp;          // (first, last) y weights
+        float wym = 0.f;     // middle y weight (TSC)
+        if (S == 2) {
+            wx[0] = 1.f - dx; wx[S - 1] = dx;
+            wz[0] = 1.f - dz; wz[S - 1] = dz;
+            wyp = make_float2(1.f - dy, dy);
+        } else {
+            const float c = 0.70710678118654752f;   // sqrt(1/2): 0.5 (0.5 -+ d)^2 = (c/2 -+ c d)^2
+            const float x0 = fmaf(-c, dx, 0.5f * c), x2 = fmaf(c, dx, 0.5f * c);
+            wx[0] = x0 * x0; wx[S / 2] = fmaf(-dx, dx, 0.75f); wx[S - 1] = x2 * x2;
+            const float z0 = fmaf(-c, dz, 0.5f * c), z2 = fmaf(c, dz, 0.5f * c);
+            wz[0] = z0 * z0; wz[S / 2] = fmaf(-dz, dz, 0.75f); wz[S - 1] = z2 * z2;
+            const float2 ty = __ffma2_rn(make_float2(-c, c), make_float2(dy, dy), make_float2(0.5f * c, 0.5f * c));
+            wyp = __fmul2_rn(ty, ty);
+            wym = fmaf(-dy, dy, 0.75f);
+        }
+        if (MASS) {
+#pragma unroll
+            for (int a = 0; a < S; ++a) wx[a] *= m;
+        }
+#pragma unroll
+        for (int a = 0; a < S; ++a) {
+            const float2 wxy = __fmul2_rn(make_float2(wx[a], wx[a]), wyp);
+            const float wxm = wx[a] * wym;
+#pragma unroll
+            for (int c = 0; c < S; ++c) {
+                A[a][c] = __ffma2_rn(wxy, make_float2(wz[c], wz[c]), A[a][c]);
+                if (S == 3) Bm[a][c] = fmaf(wxm, wz[c], Bm[a][c]);
+            }
+        }
+    }
+
+    // moment of window offset (a, b, c)
+    __device__ __forceinline__ float get(int a, int b, int c) const {
+        if (b == 0) return A[a][c].x;
+        if (b == S - 1) return A[a][c].y;
+        return Bm[a][c];
+    }
+};
+
 template <int S, bool MASS, typename VT>
 __global__ void __launch_bounds__(DEP_THREADS, 2)
 brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
@@ -203,7 +357,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);
     int *cnt = reinterpret_cast<int *>(tile + TD::SIZE);          // [BRICK_CELLS + 1]
-    int *wsum = cnt + BRICK_CELLS + 1;                            // [32] scan scratch (+ pad)
+    int *wsum = cnt + BRICK_CELLS + 1;                            // [64] scan scratch
     float *sx = reinterpret_cast<float *>(wsum + 64);
     float *sy = sx + CH;
     float *sz = sy + CH;
@@ -214,6 +368,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     const int lane = tid & 31;
     const int warp = tid >> 5;
     constexpr int OFF = (S == 3) ? 1 : 0;   // tile origin = brick origin - OFF
+    constexpr int HALF = PPT / 2;
 
     for (;;) {
         __syncthreads();
@@ -231,21 +386,28 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
             for (int i = tid; i <= BRICK_CELLS; i += DEP_THREADS) cnt[i] = 0;
             __syncthreads();   // also orders the tile zeroing / previous chunk's spreading
 
-            // ---- rank my particles inside their home cell (cell | rank << 13 kept in a register,
-            //      the coordinates are re-read from L1/L2 in the scatter pass to stay <= 64 regs)
+            // ---- rank my particles inside their home cell (cell | rank << 13 kept in a register;
+            //      the coordinates are re-read from L1/L2 in the scatter pass to stay <= 64 regs).
+            //      Loads are issued in two batches before first use to overlap their latency.
             int packed[PPT];
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                const int i = k * DEP_THREADS + tid;
-                packed[k] = -1;
-                if (i < nchunk) {
-                    const VT v = vals[c0 + i];
+            for (int h = 0; h < 2; ++h) {
+                VT v[HALF];
+#pragma unroll
+                for (int k = 0; k < HALF; ++k) {
+                    const int i = (h * HALF + k) * DEP_THREADS + tid;
+                    v[k] = vals[c0 + min(i, nchunk - 1)];
+                }
+#pragma unroll
+                for (int k = 0; k < HALF; ++k) {
+                    const int i = (h * HALF + k) * DEP_THREADS + tid;
                     int hx, hy, hz;
-                    if (S == 2) { hx = (int)floorf(v.x); hy = (int)floorf(v.y); hz = (int)floorf(v.z); }
-                    else        { hx = (int)floorf(v.x + 0.5f); hy = (int)floorf(v.y + 0.5f); hz = (int)floorf(v.z + 0.5f); }
+                    if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
+                    else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
                     hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BZ - 1));
                     const int cell = (hx * BY + hy) * BZ + hz;
-                    packed[k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
+                    packed[h * HALF + k] = -1;
+                    if (i < nchunk) packed[h * HALF + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
                 }
             }
             __syncthreads();
@@ -284,104 +446,111 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
 
             // ---- scatter into cell order --------------------------------------------------
 #pragma unroll
-            for (int k = 0; k < PPT; ++k) {
-                if (packed[k] >= 0) {
-                    const VT v = vals[c0 + k * DEP_THREADS + tid];
-                    const int slot = cnt[packed[k] & 8191] + (packed[k] >> 13);
-                    sx[slot] = v.x; sy[slot] = v.y; sz[slot] = v.z;
-                    if constexpr (MASS) sm[slot] = v.m;
+            for (int h = 0; h < 2; ++h) {
+                VT v[HALF];
+#pragma unroll
+                for (int k = 0; k < HALF; ++k) {
+                    const int i = (h * HALF + k) * DEP_THREADS + tid;
+                    v[k] = vals[c0 + min(i, nchunk - 1)];
+                }
+#pragma unroll
+                for (int k = 0; k < HALF; ++k) {
+                    const int pk = packed[h * HALF + k];
+                    if (pk >= 0) {
+                        const int slot = cnt[pk & 8191] + (pk >> 13);
+                        sx[slot] = v[k].x; sy[slot] = v[k].y; sz[slot] = v[k].z;
+                        if constexpr (MASS) sm[slot] = v[k].m;
+                    }
                 }
             }
             __syncthreads();
 
             // ---- moments per home cell, conflict-free spreading, 9 colour classes --------
+#pragma unroll 1
             for (int cls = 0; cls < 9; ++cls) {
                 const int cx = 3 * (warp >> 2) + cls / 3;
                 const int cy = 3 * (warp & 3) + cls % 3;
                 const int cell = (cx * BY + cy) * BZ + lane;
                 const int beg = cnt[cell], end = cnt[cell + 1];
-                float M[S][S][S];
-#pragma unroll
-                for (int a = 0; a < S; ++a)
-#pragma unroll
-                    for (int b = 0; b < S; ++b)
-#pragma unroll
-                        for (int c = 0; c < S; ++c) M[a][b][c] = 0.f;
-                for (int p = beg; p < end; ++p) {
-                    float wx[S], wy[S], wz[S];
-                    const float dx = sx[p] - (float)cx, dy = sy[p] - (float)cy, dz = sz[p] - (float)lane;
-                    if (S == 2) {
-                        wx[0] = 1.f - dx; wx[S - 1] = dx;
-                        wy[0] = 1.f - dy; wy[S - 1] = dy;
-                        wz[0] = 1.f - dz; wz[S - 1] = dz;
-                    } else {
-                        wx[0] = 0.5f * (0.5f - dx) * (0.5f - dx); wx[S / 2] = 0.75f - dx * dx; wx[S - 1] = 0.5f * (0.5f + dx) * (0.5f + dx);
-                        wy[0] = 0.5f * (0.5f - dy) * (0.5f - dy); wy[S / 2] = 0.75f - dy * dy; wy[S - 1] = 0.5f * (0.5f + dy) * (0.5f + dy);
-                        wz[0] = 0.5f * (0.5f - dz) * (0.5f - dz); wz[S / 2] = 0.75f - dz * dz; wz[S - 1] = 0.5f * (0.5f + dz) * (0.5f + dz);
-                    }
-                    if constexpr (MASS) {
-                        const float m = sm[p];
-#pragma unroll
-                        for (int a = 0; a < S; ++a) wx[a] *= m;
-                    }
+                if (__ballot_sync(0xffffffffu, end > beg) != 0u) {
+                    Moments<S, MASS> M;
+                    M.clear();
+                    const float fx = (float)cx, fy = (float)cy, fz = (float)lane;
+                    for (int p = beg; p < end; ++p)
+                        M.add(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? sm[p] : 1.f);
+                    // z-spread by shuffles: tile z index t = lane + jz.  The lane's own target is
+                    // t = lane + OFF; lane 0 / lane 31 also feed the two z-halo cells (one merged RMW).
+                    float *col = tile + (cx * TD::TY + cy) * TD::TZ + lane + OFF;
+                    const float up_on = lane == 0 ? 0.f : 1.f, dn_on = lane == 31 ? 0.f : 1.f;
+                    // halo cell of this lane (relative to its own target): lane 0 -> t = 0, lane 31 -> t = TZ-1
+                    const bool halo_lane = (lane == 31) || (S == 3 && lane == 0);
+                    const int halo_off = (lane == 31) ? (TD::TZ - 1) - (31 + OFF) : -OFF;
 #pragma unroll
                     for (int a = 0; a < S; ++a)
 #pragma unroll
                         for (int b = 0; b < S; ++b) {
-                            const float wxy = wx[a] * wy[b];
-#pragma unroll
-                            for (int c = 0; c < S; ++c) M[a][b][c] = fmaf(wxy, wz[c], M[a][b][c]);
-                        }
-                }
-                // z-spread by shuffles: tile z index t = lane + jz.  The lane's own target is
-                // t = lane + OFF; lane 0 / lane 31 also feed the two z-halo cells.
-                const bool any = __ballot_sync(0xffffffffu, end > beg) != 0u;
-                if (any) {
-#pragma unroll
-                    for (int a = 0; a < S; ++a)
-#pragma unroll
-                        for (int b = 0; b < S; ++b) {
-                            float own, lo_halo = 0.f, hi_halo;
+                            const float hi = M.get(a, b, S - 1), lo = M.get(a, b, 0);
+                            const float up = __shfl_up_sync(0xffffffffu, hi, 1);
+                            float own;
                             if (S == 2) {
-                                float up = __shfl_up_sync(0xffffffffu, M[a][b][S - 1], 1);
-                                if (lane == 0) up = 0.f;
-                                own = M[a][b][0] + up;
-                                hi_halo = M[a][b][S - 1];      // lane 31 -> t = 32
+                                own = fmaf(up, up_on, lo);
                             } else {
-                                float up = __shfl_up_sync(0xffffffffu, M[a][b][S - 1], 1);
-                                float dn = __shfl_down_sync(0xffffffffu, M[a][b][0], 1);
-                                if (lane == 0) up = 0.f;
-                                if (lane == 31) dn = 0.f;
-                                own = M[a][b][S / 2] + up + dn;
-                                lo_halo = M[a][b][0];          // lane 0  -> t = 0
-                                hi_halo = M[a][b][S - 1];      // lane 31 -> t = 33
+                                const float dn = __shfl_down_sync(0xffffffffu, lo, 1);
+                                own = fmaf(up, up_on, fmaf(dn, dn_on, M.get(a, b, S / 2)));
                             }
-                            float *row = tile + ((cx + a) * TD::TY + (cy + b)) * TD::TZ;
-                            row[lane + OFF] += own;
-                            if (S == 3 && lane == 0) row[0] += lo_halo;
-                            if (lane == 31) row[TD::TZ - 1] += hi_halo;
+                            float *cell_ptr = col + (a * TD::TY + b) * TD::TZ;
+                            *cell_ptr += own;
+                            if (halo_lane) cell_ptr[halo_off] += (lane == 31) ? hi : lo;
                         }
                 }
                 __syncthreads();
             }
         }
 
-        // ---- add the tile to the mesh -----------------------------------------------------
+        // ---- add the tile to the mesh: one warp per (x,y) row, RED.ADD.V2.F32 on aligned pairs ----
         const int bz = brick % B.nbz;
         const int by = (brick / B.nbz) % B.nby;
         const int bx = brick / (B.nbz * B.nby);
-        for (int i = tid; i < TD::SIZE; i += DEP_THREADS) {
-            const float v = tile[i];
-            if (v == 0.f) continue;
-            const int tz = i % TD::TZ;
-            const int ty = (i / TD::TZ) % TD::TY;
-            const int tx = i / (TD::TZ * TD::TY);
-            int px = bx * BX - OFF + tx;
-            if (G.slab) { if (px < 0 || px >= G.nplanes) continue; }
-            else px = wrap_index(px, G.N);
-            const int gy = wrap_index(by * BY - OFF + ty, G.N);
-            const int gz = wrap_index(bz * BZ - OFF + tz, G.N);
-            atomicAdd(mesh + ((size_t)px * G.N + gy) * G.ldz + gz, v);
+        const int gz0 = bz * BZ - OFF;                     // global z of tile index 0
+        const bool fast_z = gz0 >= 0 && gz0 + TD::TZ <= G.N && (G.N & 1) == 0;
+        // rows of this warp: r = warp + 16 j; lane j prepares row j's mesh offset (-1: skip)
+        constexpr int ROWS = TD::TX * TD::TY, WARPS = DEP_THREADS / 32;
+        long long my_off = -1;
+        {
+            const int r = warp + WARPS * lane;
+            if (r < ROWS) {
+                const int tx = r / TD::TY, ty = r - tx * TD::TY;
+                int px = bx * BX - OFF + tx;
+                bool ok = true;
+                if (G.slab) ok = px >= 0 && px < G.nplanes;
+                else px = wrap_index32(px, G.N);
+                const int gy = wrap_index32(by * BY - OFF + ty, G.N);
+                if (ok) my_off = ((long long)px * G.N + gy) * G.ldz;
+            }
+        }
+        for (int j = 0; warp + WARPS * j < ROWS; ++j) {
+            const long long off = __shfl_sync(0xffffffffu, my_off, j);
+            if (off < 0) continue;
+            float *grow = mesh + off;
+            const float *trow = tile + (warp + WARPS * j) * TD::TZ;
+            if (fast_z) {
+                // pairs start at tile index OFF (global z even); index 0 (TSC) and TZ-1 are single cells
+                if (lane < BZ / 2) {
+                    const float v0 = trow[OFF + 2 * lane], v1 = trow[OFF + 2 * lane + 1];
+                    if (v0 != 0.f || v1 != 0.f) red_add_v2(grow + gz0 + OFF + 2 * lane, v0, v1);
+                } else if (lane == BZ / 2) {
+                    const float v = trow[TD::TZ - 1];
+                    if (v != 0.f) atomicAdd(grow + gz0 + TD::TZ - 1, v);
+                } else if (S == 3 && lane == BZ / 2 + 1) {
+                    const float v = trow[0];
+                    if (v != 0.f) atomicAdd(grow + gz0, v);
+                }
+            } else {
+                for (int tz = lane; tz < TD::TZ; tz += 32) {
+                    const float v = trow[tz];
+                    if (v != 0.f) atomicAdd(grow + wrap_index32(gz0 + tz, G.N), v);
+                }
+            }
         }
     }
 }
@@ -419,13 +588,18 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)P->num_sms * 8);
     P->mark(0, st);
     APK_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)(B.nbricks + 1), st));
-    brick_count_kernel<S, PT, SOA><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
+    constexpr bool CANVEC = std::is_same<PT, float>::value;
+    const bool vec = CANVEC && ((((uintptr_t)p0) | (SOA ? ((uintptr_t)p1 | (uintptr_t)p2) : 0)) & 15) == 0;
+    if (vec) brick_count_kernel<S, PT, SOA, CANVEC><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
+    else brick_count_kernel<S, PT, SOA, false><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
     APK_CUDA(cudaGetLastError());
     P->mark(1, st);
     brick_scan_kernel<<<1, 1024, 0, st>>>(counts, B.nbricks, brick_start, cursor);
     APK_CUDA(cudaGetLastError());
     P->mark(2, st);
-    brick_scatter_kernel<S, PT, SOA, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
+    if (vec) brick_scatter_kernel<S, PT, SOA, CANVEC, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
+        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
+    else brick_scatter_kernel<S, PT, SOA, false, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
         (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
     APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));

@@ -37,6 +37,9 @@ WORKLOADS = {
     "c3": dict(n=1024, mesh=1024, box=1000.0, resampler="tsc", interlaced=True, compensated=True, seed=31337,
                kind="zeldovich", name="c3: 1024^3 Zel'dovich particles, TSC + interlacing + compensation, 1024^3 mesh"),
 }
+# diagnostics only (not BASELINE configs): a half-size c3 for profiling, and an incoherent-order c2
+WORKLOADS["c3s"] = dict(WORKLOADS["c3"], n=512, mesh=512, name="c3s: 512^3 particles, TSC + interlacing + compensation, 512^3 mesh (profiling)")
+WORKLOADS["c2u"] = dict(WORKLOADS["c2"], kind="uniform", name="c2u: 512^3 uniform-random particles (incoherent order), CIC, 512^3 mesh")
 METRIC = "P(k) pipeline Mparticles/s (deposit+FFT+binning)"
 UNIT = "Mparticles/s"
 
