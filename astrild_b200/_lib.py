@@ -39,6 +39,8 @@ SIGNATURES = {
     "apk_plan_last_deposit_ms": [_vp, ct.POINTER(ct.c_float)],
     "apk_binning_last_ms": [_vp, ct.POINTER(ct.c_float)],
     "apk_deposit": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _d, _i, _i, _vp, _vp],
+    "apk_route_particles": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp],
+    "apk_mesh_accumulate": [_vp, _vp, _vp, _i64, _vp],
     "apk_mesh_sum": [_vp, _vp, _i, _vp, _vp],
     "apk_padded_mesh_sum": [_vp, _vp, _vp, _vp],
     "apk_load_mesh": [_vp, _vp, _i, _d, _vp, _vp],
@@ -46,6 +48,7 @@ SIGNATURES = {
     "apk_fft_r2c": [_vp, _vp, _vp],
     "apk_fft_r2c_2d": [_vp, _vp, _vp],
     "apk_fft_c2c_1d": [_vp, _vp, _i, _vp],
+    "apk_plan_prepare_fft1d": [_vp, _i],
     "apk_binning_create": [ct.POINTER(_vp), _vp, _i, _i, _i] + [_vp] * 5 + [_i] + [_vp] * 6 + [_i, _i],
     "apk_binning_destroy": [_vp],
     "apk_bin_power": [_vp] * 9 + [_vp],

@@ -27,6 +27,9 @@ int mesh_sum_launch(apk_plan *, const void *, int, double *, cudaStream_t);
 int padded_mesh_sum_launch(apk_plan *, const float *, double *, cudaStream_t);
 int load_mesh_launch(apk_plan *, const void *, int, double, float *, cudaStream_t);
 int store_mesh_launch(apk_plan *, const float *, double, double *, cudaStream_t);
+int route_launch(apk_plan *, const void *, const void *, const void *, int, int, double, const void *, int, long long,
+                 int, unsigned long long *, void *, void *, cudaStream_t);
+int accumulate_launch(apk_plan *, float *, const float *, long long, cudaStream_t);
 int bin_power_launch(apk_binning *, const void *, const void *, const void *, const void *, double *,
                      double *, double *, int64_t *, cudaStream_t);
 
@@ -207,6 +210,24 @@ int apk_binning_last_ms(apk_binning *B, float ms[2]) {
     return 0;
 }
 
+int apk_route_particles(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
+                        double pos_scale, const void *mass, int mass_dtype, int64_t np, int nranks,
+                        uint64_t *counts_dev, void *out_pos, void *out_mass, void *stream) {
+    APK_REQUIRE(P && counts_dev && (np == 0 || (p0 && out_pos)), "apk_route_particles: null argument");
+    APK_REQUIRE(layout == APK_AOS || (p1 && p2) || np == 0, "apk_route_particles: SoA layout needs three pointers");
+    APK_REQUIRE(pos_dtype == APK_F32 || pos_dtype == APK_F64, "apk_route_particles: bad position dtype %d", pos_dtype);
+    APK_REQUIRE(!mass || out_mass, "apk_route_particles: mass given without out_mass");
+    DeviceGuard guard(P->device);
+    return route_launch(P, p0, p1, p2, layout, pos_dtype, pos_scale, mass, mass_dtype, np, nranks,
+                        (unsigned long long *)counts_dev, out_pos, out_mass, (cudaStream_t)stream);
+}
+
+int apk_mesh_accumulate(apk_plan *P, float *dst, const float *src, int64_t n, void *stream) {
+    APK_REQUIRE(P && dst && src, "apk_mesh_accumulate: null argument");
+    DeviceGuard guard(P->device);
+    return accumulate_launch(P, dst, src, n, (cudaStream_t)stream);
+}
+
 int apk_mesh_sum(apk_plan *P, const void *value_map, int dtype, double *sum_dev, void *stream) {
     APK_REQUIRE(P && value_map && sum_dev, "apk_mesh_sum: null argument");
     DeviceGuard guard(P->device);
@@ -260,6 +281,12 @@ int apk_fft_r2c_2d(apk_plan *P, float *mesh, void *stream) {
     if (P->fft_work_bytes) APK_CUFFT(cufftSetWorkArea(P->fft2d, P->workspace));
     APK_CUFFT(cufftExecR2C(P->fft2d, mesh, (cufftComplex *)mesh));
     return 0;
+}
+
+int apk_plan_prepare_fft1d(apk_plan *P, int ny_local) {
+    APK_REQUIRE(P && ny_local >= 1, "apk_plan_prepare_fft1d: bad argument");
+    DeviceGuard guard(P->device);
+    return make_fft1d(P, ny_local);
 }
 
 int apk_fft_c2c_1d(apk_plan *P, void *grid, int ny_local, void *stream) {

@@ -1,0 +1,131 @@
+// Slab routing of particles and ghost-plane accumulation for the multi-GPU path.
+//
+// The reference has no multi-rank path (astrild runs pmesh/nbodykit on one rank;
+// /root/reference/src/astrild/particles/hutils/stats_subfind.py:130 builds the ParticleMesh
+// without a communicator).  pmesh's own decomposition (domain.GridND + exchange) is what this
+// replaces: every particle goes to the rank whose x-slab holds floor(g_x), g = pos*pos_scale*N,
+// using the same float64 index arithmetic as the deposit so a particle never lands outside the
+// ghost planes of the slab it was routed to.
+//
+// Bound: HBM; bytes = np * 3 * sizeof(pos) read + written (+ mass).  Snapshot order is spatially
+// coherent, so per-destination counters are updated once per warp-run of equal destinations.
+#include "apk_common.cuh"
+#include "deposit_common.cuh"
+#include <algorithm>
+
+namespace apk {
+
+__device__ __forceinline__ void warp_runs_r(int key, int lane, int &head, int &offset, int &length) {
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const unsigned int heads = __ballot_sync(0xffffffffu, lane == 0 || key != prev);
+    const unsigned int below = heads & ((2u << lane) - 1u);
+    head = 31 - __clz(below);
+    offset = lane - head;
+    const unsigned int above = heads & ~((2u << lane) - 1u);
+    length = (above ? __ffs(above) - 1 : 32) - head;
+}
+
+template <typename PT, bool SOA>
+__device__ __forceinline__ int dest_rank(const PT *__restrict__ p0, long long p, double scale, int N, int planes_per_rank) {
+    const double g = (double)(SOA ? p0[p] : p0[3 * p]) * scale;
+    long long i = (long long)floor(g);
+    return wrap_index(i, N) / planes_per_rank;
+}
+
+template <typename PT, bool SOA>
+__global__ void __launch_bounds__(256)
+route_count_kernel(const PT *__restrict__ p0, long long np, double scale, int N, int ppr,
+                   unsigned long long *__restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long np_pad = (np + 31) & ~31LL;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += stride) {
+        const int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
+        int head, offset, length;
+        warp_runs_r(d, lane, head, offset, length);
+        if (d >= 0 && offset == 0) atomicAdd(counts + d, (unsigned long long)length);
+    }
+}
+
+// counts[P] -> cursor[P] = exclusive scan (P <= 1024)
+__global__ void route_scan_kernel(const unsigned long long *counts, int P, unsigned long long *cursor) {
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < P; ++i) { cursor[i] = run; run += counts[i]; }
+    }
+}
+
+template <typename PT, bool SOA, typename MT>
+__global__ void __launch_bounds__(256)
+route_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
+                     const MT *__restrict__ mass, long long np, double scale, int N, int ppr,
+                     unsigned long long *__restrict__ cursor, PT *__restrict__ out_pos, MT *__restrict__ out_mass) {
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long np_pad = (np + 31) & ~31LL;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += stride) {
+        const int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
+        int head, offset, length;
+        warp_runs_r(d, lane, head, offset, length);
+        unsigned long long slot = 0;
+        if (d >= 0 && offset == 0) slot = atomicAdd(cursor + d, (unsigned long long)length);
+        slot = __shfl_sync(0xffffffffu, slot, head) + offset;
+        if (d >= 0) {
+            PT x, y, z;
+            if (SOA) { x = p0[p]; y = p1[p]; z = p2[p]; }
+            else     { x = p0[3 * p]; y = p0[3 * p + 1]; z = p0[3 * p + 2]; }
+            out_pos[3 * slot] = x; out_pos[3 * slot + 1] = y; out_pos[3 * slot + 2] = z;
+            if (mass) out_mass[slot] = mass[p];
+        }
+    }
+}
+
+template <typename PT, bool SOA, typename MT>
+static int route_typed(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass, long long np,
+                       double pos_scale, int nranks, unsigned long long *counts, void *out_pos, void *out_mass,
+                       cudaStream_t st) {
+    const int ppr = P->N / nranks;
+    const double scale = pos_scale * (double)P->N;
+    unsigned long long *cursor = counts + nranks;
+    APK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * nranks, st));
+    if (np > 0) {
+        const int blocks = (int)std::min<long long>((np + 255) / 256, (long long)P->num_sms * 16);
+        route_count_kernel<PT, SOA><<<blocks, 256, 0, st>>>((const PT *)p0, np, scale, P->N, ppr, counts);
+        APK_CUDA(cudaGetLastError());
+        route_scan_kernel<<<1, 32, 0, st>>>(counts, nranks, cursor);
+        APK_CUDA(cudaGetLastError());
+        route_scatter_kernel<PT, SOA, MT><<<blocks, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2,
+                                                                  (const MT *)mass, np, scale, P->N, ppr, cursor,
+                                                                  (PT *)out_pos, (MT *)out_mass);
+        APK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int route_launch(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
+                 double pos_scale, const void *mass, int mass_dtype, long long np, int nranks,
+                 unsigned long long *counts, void *out_pos, void *out_mass, cudaStream_t st) {
+    APK_REQUIRE(nranks >= 1 && nranks <= 1024 && P->N % nranks == 0, "apk_route_particles: nmesh %d not divisible by %d ranks", P->N, nranks);
+    APK_REQUIRE(!mass || mass_dtype == pos_dtype, "apk_route_particles: mass must have the dtype of the positions");
+    const bool soa = layout == APK_SOA;
+    if (pos_dtype == APK_F32)
+        return soa ? route_typed<float, true, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st)
+                   : route_typed<float, false, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st);
+    return soa ? route_typed<double, true, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st)
+               : route_typed<double, false, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st);
+}
+
+__global__ void __launch_bounds__(256) accumulate_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
+
+int accumulate_launch(apk_plan *P, float *dst, const float *src, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)P->num_sms * 8);
+    accumulate_kernel<<<blocks, 256, 0, st>>>(dst, src, n);
+    APK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace apk

@@ -1,0 +1,261 @@
+"""Slab-decomposed P(k) across the GPUs of one node: one process per GPU, torch.distributed/NCCL.
+
+astrild itself is single-rank; the MPI decomposition lives unused inside
+pmesh/pfft.  This module is the B200 counterpart of that decomposition for the same path
+(/root/reference/src/astrild/particles/hutils/stats_subfind.py:125-150):
+
+  1. route      every particle to the rank owning the x-slab of floor(g_x)   (all-to-all-v)
+  2. deposit    into [1 ghost | n0 owned | 2 ghost] planes                    (local kernel)
+  3. ghosts     ghost planes -> ring neighbours, added to their owned planes  (send/recv)
+  4. 2-D r2c    over (y, z) on the owned planes                               (cuFFT, local)
+  5. transpose  x <-> y: rank s receives y in [s N/P, (s+1) N/P) for all x     (all-to-all)
+  6. 1-D c2c    along x                                                        (cuFFT, local)
+  7. binning    fused kernel on the transposed [x][y_local][z] grid            (local kernel)
+  8. reduce     shell sums, mode counts and total mass                         (all-reduce)
+
+Nothing is transposed back: the binning kernel only needs per-axis k tables (exactly what
+pfft's PFFT_TRANSPOSED_OUT gives nbodykit).  Mode counts are integers, so they are identical to
+the single-GPU result; the float64 sums differ only in summation order.
+
+The compute stages go through a *backend* object; the product backend is CudaSlabBackend
+(libastrild_pk.so).  tests/ inject a NumPy backend to exercise this file's exchange logic with the
+gloo backend on CPUs -- that backend lives in tests/, never here.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib, tables
+from ._lib import AstrildPkError
+from .engine import PkEngine, _ptr
+
+
+class CudaSlabBackend:
+    """Compute stages of one rank on its GPU (libastrild_pk.so)."""
+
+    def __init__(self, N: int, L: float, x0: int, n0: int, nranks: int, device):
+        self.eng = PkEngine(N, L, device, x0=x0, n0=n0)
+        self.device = self.eng.device
+        self.N, self.L, self.n0, self.nranks = N, L, n0, nranks
+        self._counts = torch.zeros(2 * nranks, dtype=torch.int64, device=self.device)
+
+    # -- 1. routing -----------------------------------------------------------------------
+    def route(self, pos, mass, pos_scale: float):
+        eng = self.eng
+        p0, p1, p2, layout, dt, npart, keep = eng._positions(pos)
+        m = None
+        if mass is not None:
+            m = eng._to_device(mass).to(dt).contiguous()
+        out_pos = torch.empty((npart, 3), dtype=dt, device=self.device)
+        out_mass = torch.empty(npart, dtype=dt, device=self.device) if m is not None else None
+        code = _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64
+        _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),
+                  _ptr(m), code, int(npart), self.nranks, _ptr(self._counts), _ptr(out_pos), _ptr(out_mass), eng.stream)
+        counts = self._counts[: self.nranks].cpu().tolist()
+        del keep
+        return out_pos, out_mass, counts
+
+    def empty_like_rows(self, like: torch.Tensor, rows: int) -> torch.Tensor:
+        return torch.empty((rows,) + tuple(like.shape[1:]), dtype=like.dtype, device=self.device)
+
+    # -- 2./3. deposit and ghost planes ---------------------------------------------------------
+    def deposit(self, pos_aos, mass, resampler: str, shift: float, pos_scale: float):
+        return self.eng.deposit(pos_aos, mass, resampler, shift, pos_scale, "auto")
+
+    def accumulate(self, dst: torch.Tensor, src: torch.Tensor) -> None:
+        assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
+        _lib.call("apk_mesh_accumulate", self.eng._plan, _ptr(dst), _ptr(src), dst.numel(), self.eng.stream)
+
+    def mesh_sum(self, owned: torch.Tensor) -> torch.Tensor:
+        out = torch.zeros(1, dtype=torch.float64, device=self.device)
+        _lib.call("apk_padded_mesh_sum", self.eng._plan, _ptr(owned), _ptr(out), self.eng.stream)
+        return out
+
+    # -- 4./6. FFT stages ---------------------------------------------------------------------------
+    def fft2d(self, owned: torch.Tensor) -> torch.Tensor:
+        eng = self.eng
+        eng.ensure_workspace(0, False)
+        _lib.call("apk_fft_r2c_2d", eng._plan, _ptr(owned), eng.stream)
+        return torch.view_as_complex(owned.view(self.n0, self.N, eng.Nk, 2))
+
+    def fft1d(self, grid: torch.Tensor, ny: int) -> torch.Tensor:
+        eng = self.eng
+        _lib.call("apk_plan_prepare_fft1d", eng._plan, int(ny))     # plan first: it sizes the workspace
+        eng.ensure_workspace(0, False)
+        _lib.call("apk_fft_c2c_1d", eng._plan, _ptr(grid), int(ny), eng.stream)
+        return grid
+
+    # -- 7. binning ----------------------------------------------------------------------------------
+    def make_binning(self, y0: int, ny: int, kmin, dk, kmax, compensation, interlaced):
+        axes = {"ia": np.arange(self.N), "ib": np.arange(y0, y0 + ny), "key": ("slabT", y0, ny)}
+        return self.eng.binning(kmin, dk, kmax, compensation, interlaced, axes=axes)
+
+    def bin(self, binning, c1, c1s) -> torch.Tensor:
+        return self.eng.bin_power_raw(binning, c1, c1s)
+
+    def to_reduce_tensor(self, raw, total_mass) -> torch.Tensor:
+        """[ksum | psum_re | psum_im | nmodes as float64 | total mass] for ONE all-reduce."""
+        nb1 = raw.shape[1]
+        out = torch.empty(4 * nb1 + 1, dtype=torch.float64, device=self.device)
+        out[: 3 * nb1] = raw[:3].reshape(-1)
+        out[3 * nb1: 4 * nb1] = raw[3].view(torch.int64).to(torch.float64)      # exact below 2^53
+        out[4 * nb1] = total_mass[0]
+        return out
+
+
+class TorchDistComm:
+    """The four exchanges of the path over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.P = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def _global(self, r: int) -> int:
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def all_to_all_rows(self, send: torch.Tensor, send_counts: list, alloc) -> torch.Tensor:
+        """all-to-all-v of the leading dimension; alloc(rows) makes the receive buffer."""
+        sc = torch.tensor(send_counts, dtype=torch.int64, device=send.device)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        recv_counts = rc.cpu().tolist()
+        recv = alloc(int(sum(recv_counts)))
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                               group=self.group)
+        return recv
+
+    def ring_exchange(self, to_prev: torch.Tensor, to_next: torch.Tensor):
+        """Send to_prev to rank-1 and to_next to rank+1; returns (from_next, from_prev)."""
+        prev, nxt = self._global((self.rank - 1) % self.P), self._global((self.rank + 1) % self.P)
+        from_next, from_prev = torch.empty_like(to_prev), torch.empty_like(to_next)
+        # with two ranks prev == nxt: receives are posted in the order the peer sends (lo, then hi)
+        ops = [dist.P2POp(dist.isend, to_prev, prev, self.group), dist.P2POp(dist.isend, to_next, nxt, self.group),
+               dist.P2POp(dist.irecv, from_next, nxt, self.group), dist.P2POp(dist.irecv, from_prev, prev, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return from_next, from_prev
+
+    def all_to_all_blocks(self, send: torch.Tensor) -> torch.Tensor:
+        """send[s] goes to rank s; returns recv with recv[q] = what rank q sent here (equal blocks)."""
+        recv = torch.empty_like(send)
+        if send.is_complex():
+            dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), group=self.group)
+        else:
+            dist.all_to_all_single(recv, send, group=self.group)
+        return recv
+
+    def all_reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class SlabPk:
+    """P(k) of particles distributed over the ranks of ``comm`` (default: the torch.distributed world)."""
+
+    def __init__(self, Nmesh: int, BoxSize: float, resampler: str = "tsc", interlaced: bool = False,
+                 compensated: bool = False, device=None, group=None, backend=None, comm=None):
+        self.comm = comm if comm is not None else TorchDistComm(group)
+        self.P, self.rank = self.comm.P, self.comm.rank
+        self.N, self.L = int(Nmesh), float(BoxSize)
+        if self.N % self.P:
+            raise AstrildPkError(f"Nmesh {self.N} must be divisible by the number of ranks {self.P}")
+        self.n0 = self.N // self.P
+        self.x0 = self.rank * self.n0
+        self.ny, self.y0 = self.n0, self.x0              # after the transpose this rank owns these y
+        self.Nk = self.N // 2 + 1
+        self.resampler, self.interlaced, self.compensated = str(resampler).lower(), bool(interlaced), bool(compensated)
+        if backend is None:
+            backend = CudaSlabBackend(self.N, self.L, self.x0, self.n0, self.P, device)
+        self.backend = backend
+        self.eng = getattr(backend, "eng", None)
+        self.ghost_lo, self.ghost_hi = 1, 2
+        if self.P > 1 and self.n0 < 2:
+            raise AstrildPkError("each rank needs at least 2 mesh planes")
+
+    # ------------------------------------------------------------------ helpers
+    def lattice_planes(self, n: int) -> tuple:
+        """Planes [a, b) of an n^3 lattice this rank generates (contiguous, near its own slab)."""
+        a = (self.rank * n) // self.P
+        b = ((self.rank + 1) * n) // self.P
+        return a, b
+
+    def _exchange_ghosts(self, mesh: torch.Tensor) -> torch.Tensor:
+        """Send ghost planes to the ring neighbours, add what arrives; returns the owned planes."""
+        lo, hi, n0 = self.ghost_lo, self.ghost_hi, self.n0
+        if self.P == 1:
+            return mesh                                  # whole periodic mesh: the kernel wrapped already
+        owned = mesh[lo: lo + n0]
+        # ghost_lo is the previous rank's last plane, ghost_hi the next rank's first planes
+        from_next, from_prev = self.comm.ring_exchange(mesh[:lo].contiguous(), mesh[lo + n0:].contiguous())
+        self.backend.accumulate(owned[n0 - lo:], from_next)
+        self.backend.accumulate(owned[:hi], from_prev)
+        return owned
+
+    def _transpose(self, grids: list) -> list:
+        """[n0][N][Nk] x-slabs -> [N][ny][Nk] y-slabs; one all-to-all per field so that the
+        received blocks (ordered by source rank = by x) already are the transposed slab."""
+        P, n0, ny, Nk = self.P, self.n0, self.ny, self.Nk
+        out = []
+        for g in grids:
+            # block for rank s: [x_local][y in s's range][z]
+            send = g.reshape(n0, P, ny, Nk).permute(1, 0, 2, 3).contiguous()     # [P][n0][ny][Nk]
+            recv = send if P == 1 else self.comm.all_to_all_blocks(send)
+            out.append(recv.reshape(self.N, ny, Nk))
+        return out
+
+    # ------------------------------------------------------------------ the path
+    def power(self, pos, mass=None, pos_scale: float | None = None, kmin: float = 0.0, dk=None, kmax=None,
+              normalize: bool = True, routed: bool = False) -> dict:
+        """(k, power, modes) of this rank's particles together with everyone else's.
+
+        pos: this rank's share, (Np,3) or three columns, host or device.  routed=True promises that
+        every particle already sits on the rank owning floor(g_x) (skips the all-to-all-v).
+        """
+        be, P = self.backend, self.P
+        ps = 1.0 / self.L if pos_scale is None else float(pos_scale)
+        # 1. route
+        if routed or P == 1:
+            rp, rm = pos, mass
+        else:
+            sp, sm, counts = be.route(pos, mass, ps)
+            rp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
+            rm = self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows)) if sm is not None else None
+            del sp, sm
+        # 2./3. deposit + ghosts
+        shifts = (0.0, 0.5) if self.interlaced else (0.0,)
+        owned = []
+        for sh in shifts:
+            mesh = be.deposit(rp, rm, self.resampler, sh, ps)
+            owned.append(self._exchange_ghosts(mesh))
+        total = be.mesh_sum(owned[0])
+        # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
+        grids = [be.fft2d(o) for o in owned]
+        grids = self._transpose(grids)
+        del owned
+        grids = [be.fft1d(g, self.ny) for g in grids]
+        # 7. binning on the transposed slab
+        comp = (self.resampler, self.interlaced) if self.compensated else None
+        binning = be.make_binning(self.y0, self.ny, kmin, dk, kmax, comp, self.interlaced)
+        raw = be.bin(binning, grids[0], grids[1] if self.interlaced else None)
+        # 8. reduce
+        red = be.to_reduce_tensor(raw, total)
+        if P > 1:
+            red = self.comm.all_reduce_sum(red)
+        host = red.cpu().numpy()
+        nb1 = (len(host) - 1) // 4
+        ksum, pre, pim = host[:nb1], host[nb1:2 * nb1], host[2 * nb1:3 * nb1]
+        nsum = np.rint(host[3 * nb1:4 * nb1]).astype(np.int64)
+        W = host[4 * nb1]
+        N, L = self.N, self.L
+        field_scale = (N ** 3 / W) if normalize else 1.0 / (L / N) ** 3
+        scale = L ** 3 * field_scale ** 2 / float(N) ** 6
+        with np.errstate(invalid="ignore", divide="ignore"):
+            k = (ksum / nsum)[1:-1]
+            power = ((pre + 1j * pim) * scale / nsum)[1:-1]
+        return {"k": k, "power": power, "modes": nsum[1:-1].copy(), "edges": binning.edges, "Nsum": nsum,
+                "total_mass": W}

@@ -84,6 +84,19 @@ int apk_deposit(apk_plan *plan, const void *p0, const void *p1, const void *p2, 
                 int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
                 int resampler, double shift, int method, int zero_first, float *mesh, void *stream);
 
+/* ---- slab routing (multi-GPU) ---------------------------------------------------------------- */
+/* Orders the particles by destination rank = owner of the x-slab holding floor(pos_x*pos_scale*N)
+ * (N/nranks planes per rank, N divisible by nranks).  Writes positions as AoS (np,3) of the input
+ * dtype into out_pos (and masses, same dtype, into out_mass when mass != NULL) grouped by
+ * destination, and the per-destination counts into counts_dev[0..nranks) (uint64; the array must
+ * hold 2*nranks entries, the second half is scratch).  The host reads the counts to size the
+ * all-to-all.  pmesh equivalent: ParticleMesh.decompose + layout.exchange (unused by astrild).   */
+int apk_route_particles(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
+                        int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
+                        int nranks, uint64_t *counts_dev, void *out_pos, void *out_mass, void *stream);
+/* dst[i] += src[i], i < n: adds received ghost planes into the owned slab                       */
+int apk_mesh_accumulate(apk_plan *plan, float *dst, const float *src, int64_t n, void *stream);
+
 /* ---- ArrayMesh: gridded field -> mesh ------------------------------------------------------ */
 /* value_map: contiguous [n0][N][N] of dtype; writes (value - mean_subtract) as f32 into the
  * padded mesh.  apk_mesh_sum gives the f64 sum of a value_map (for the mean).                 */
@@ -102,6 +115,8 @@ int apk_fft_r2c(apk_plan *plan, float *mesh, void *stream);
 /* slab stages: batched 2-D r2c over (y,z) of n0 local planes, and batched 1-D c2c along the
  * leading axis of a [N][ny_local][N/2+1] array.                                              */
 int apk_fft_r2c_2d(apk_plan *plan, float *mesh, void *stream);
+/* creates the 1-D plan for ny_local ahead of time so apk_plan_workspace_bytes accounts for it  */
+int apk_plan_prepare_fft1d(apk_plan *plan, int ny_local);
 int apk_fft_c2c_1d(apk_plan *plan, void *grid, int ny_local, void *stream);
 
 /* ---- binning (FFTPower mode="1d") ---------------------------------------------------------- */
