@@ -65,7 +65,7 @@ class ThreadComm:
         return total
 
 
-def _run_emulated(P, N, L, pos, mass, **kw):
+def _run_emulated(P, N, L, pos, mass, kw):
     from astrild_b200 import distributed
     shared = ThreadComm.Shared(P)
     results, errors = [None] * P, []
@@ -107,7 +107,7 @@ def test_slab_path_matches_oracle_and_single_gpu(oracle_fast, P, kw):
                                             compensated=kw["compensated"], normalize=kw["normalize"])
     single = ab.FFTPower(ab.CatalogMesh(pos, L, N, weight=mass, resampler=kw["resampler"], interlaced=kw["interlaced"],
                                         compensated=kw["compensated"], normalize=kw["normalize"]), mode="1d", kmin=2 * np.pi / L)
-    for res in _run_emulated(P, N, L, pos, mass, **kw):
+    for res in _run_emulated(P, N, L, pos, mass, kw):
         np.testing.assert_array_equal(res["modes"], want[2])                       # bit-exact, any P
         np.testing.assert_array_equal(res["modes"], single.power["modes"])
         np.testing.assert_allclose(res["k"], want[0], rtol=1e-12)
@@ -123,7 +123,7 @@ def test_slab_path_large_sorted_deposit(oracle_fast):
     kw = dict(resampler="tsc", interlaced=True, compensated=True, normalize=True, mass=False)
     want = oracle_fast.power_from_particles(pos, None, N, L, resampler="tsc", interlaced=True, compensated=True,
                                             normalize=True, threads=4, workers=4)
-    for res in _run_emulated(2, N, L, pos, None, **kw):
+    for res in _run_emulated(2, N, L, pos, None, kw):
         np.testing.assert_array_equal(res["modes"], want[2])
         np.testing.assert_allclose(res["power"].real, want[1], rtol=1e-4)
 
