@@ -39,7 +39,7 @@ SIGNATURES = {
     "apk_plan_last_deposit_ms": [_vp, ct.POINTER(ct.c_float)],
     "apk_binning_last_ms": [_vp, ct.POINTER(ct.c_float)],
     "apk_deposit": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _d, _i, _i, _vp, _vp],
-    "apk_route_particles": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp],
+    "apk_route_particles": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp],
     "apk_mesh_accumulate": [_vp, _vp, _vp, _i64, _vp],
     "apk_mesh_sum": [_vp, _vp, _i, _vp, _vp],
     "apk_padded_mesh_sum": [_vp, _vp, _vp, _vp],

@@ -28,7 +28,7 @@ int padded_mesh_sum_launch(apk_plan *, const float *, double *, cudaStream_t);
 int load_mesh_launch(apk_plan *, const void *, int, double, float *, cudaStream_t);
 int store_mesh_launch(apk_plan *, const float *, double, double *, cudaStream_t);
 int route_launch(apk_plan *, const void *, const void *, const void *, int, int, double, const void *, int, long long,
-                 int, unsigned long long *, void *, void *, cudaStream_t);
+                 int, unsigned long long *, long long, void *, void *, cudaStream_t);
 int accumulate_launch(apk_plan *, float *, const float *, long long, cudaStream_t);
 int bin_power_launch(apk_binning *, const void *, const void *, const void *, const void *, double *,
                      double *, double *, int64_t *, cudaStream_t);
@@ -166,6 +166,7 @@ int apk_deposit(apk_plan *P, const void *p0, const void *p1, const void *p2, int
     DepositGeom G;
     G.N = P->N; G.ldz = P->ldz; G.scale = pos_scale * (double)P->N; G.shift = shift;
     G.slab = P->n0 < P->N; G.plane0 = P->x0 - P->ghost_lo; G.nplanes = P->ghost_lo + P->n0 + P->ghost_hi;
+    G.own0 = P->x0; G.nown = P->n0;
     if (zero_first)
         APK_CUDA(cudaMemsetAsync(mesh, 0, sizeof(float) * (size_t)G.nplanes * P->N * P->ldz, st));
     if (method == APK_DEPOSIT_AUTO)
@@ -212,14 +213,14 @@ int apk_binning_last_ms(apk_binning *B, float ms[2]) {
 
 int apk_route_particles(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
                         double pos_scale, const void *mass, int mass_dtype, int64_t np, int nranks,
-                        uint64_t *counts_dev, void *out_pos, void *out_mass, void *stream) {
-    APK_REQUIRE(P && counts_dev && (np == 0 || (p0 && out_pos)), "apk_route_particles: null argument");
+                        uint64_t *counts_dev, int64_t capacity, void *out_pos, void *out_mass, void *stream) {
+    APK_REQUIRE(P && counts_dev && (np == 0 || p0) && (capacity == 0 || out_pos), "apk_route_particles: null argument");
     APK_REQUIRE(layout == APK_AOS || (p1 && p2) || np == 0, "apk_route_particles: SoA layout needs three pointers");
     APK_REQUIRE(pos_dtype == APK_F32 || pos_dtype == APK_F64, "apk_route_particles: bad position dtype %d", pos_dtype);
     APK_REQUIRE(!mass || out_mass, "apk_route_particles: mass given without out_mass");
     DeviceGuard guard(P->device);
     return route_launch(P, p0, p1, p2, layout, pos_dtype, pos_scale, mass, mass_dtype, np, nranks,
-                        (unsigned long long *)counts_dev, out_pos, out_mass, (cudaStream_t)stream);
+                        (unsigned long long *)counts_dev, capacity, out_pos, out_mass, (cudaStream_t)stream);
 }
 
 int apk_mesh_accumulate(apk_plan *P, float *dst, const float *src, int64_t n, void *stream) {

@@ -22,6 +22,7 @@ deposit_atomic_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, cons
         double x, y, z;
         if (SOA) { x = (double)p0[p]; y = (double)p1[p]; z = (double)p2[p]; }
         else     { x = (double)p0[3 * p]; y = (double)p0[3 * p + 1]; z = (double)p0[3 * p + 2]; }
+        if (!owned_by_slab(x * G.scale, G)) continue;   // slab plans: another rank deposits it
         float m = 1.f;
         if (mass) m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
         long long ix, iy, iz;

@@ -13,6 +13,8 @@ struct DepositGeom {
     int slab;       // 0: whole periodic mesh, 1: slab with ghost planes
     int plane0;     // global index of local plane 0 (x0 - ghost_lo), may be negative
     int nplanes;    // local planes (ghost_lo + n0 + ghost_hi), == N when !slab
+    int own0;       // first owned plane x0
+    int nown;       // owned planes n0; slab plans deposit only particles with floor(g_x - shift) owned
 
     __host__ __device__ __forceinline__ int local_plane(long long ix) const;
 };
@@ -32,6 +34,13 @@ __host__ __device__ __forceinline__ int DepositGeom::local_plane(long long ix) c
     if (rel < 0) rel += N;
     else if (rel >= N) rel -= N;
     return rel < nplanes ? rel : -1;
+}
+
+// slab ownership of a particle: floor of its UNSHIFTED grid coordinate lies in [own0, own0 + nown)
+__device__ __forceinline__ bool owned_by_slab(double gx_unshifted, const DepositGeom &G) {
+    if (!G.slab) return true;
+    int rel = wrap_index((long long)floor(gx_unshifted), G.N) - G.own0;
+    return rel >= 0 && rel < G.nown;
 }
 
 // base index and weights of pmesh's window of support S at grid coordinate g

@@ -88,6 +88,7 @@ __device__ __forceinline__ int wrap_index32(int i, int N) {
 template <int S>
 __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const DepositGeom &G,
                                                  const BrickGrid &B, float (&l)[3]) {
+    if (!owned_by_slab(x[0] * G.scale, G)) return 0xffffffffu;         // slab plans: not this rank's particle
     int b[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -99,7 +100,7 @@ __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const Dep
         if (d == 0 && G.slab) {
             hl -= G.plane0;
             if (hl < 0) hl += G.N; else if (hl >= G.N) hl -= G.N;
-            if (hl >= G.nplanes) hl = 0;                                // not routed here: caller error
+            if (hl >= G.nplanes) hl = 0;                                // unreachable for owned particles
         }
         const int edge = d == 0 ? BX : (d == 1 ? BY : BZ);
         b[d] = hl / edge;

@@ -32,15 +32,19 @@ __device__ __forceinline__ int dest_rank(const PT *__restrict__ p0, long long p,
     return wrap_index(i, N) / planes_per_rank;
 }
 
+// pass 1: how many of my particles belong to each OTHER rank (the ones that stay are not touched:
+// the slab deposit skips particles it does not own, so only leavers are copied and sent)
 template <typename PT, bool SOA>
 __global__ void __launch_bounds__(256)
-route_count_kernel(const PT *__restrict__ p0, long long np, double scale, int N, int ppr,
+route_count_kernel(const PT *__restrict__ p0, long long np, double scale, int N, int ppr, int self,
                    unsigned long long *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long np_pad = (np + 31) & ~31LL;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += stride) {
-        const int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
+        int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
+        if (d == self) d = -1;
+        if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;        // the usual case: nobody leaves
         int head, offset, length;
         warp_runs_r(d, lane, head, offset, length);
         if (d >= 0 && offset == 0) atomicAdd(counts + d, (unsigned long long)length);
@@ -58,19 +62,22 @@ __global__ void route_scan_kernel(const unsigned long long *counts, int P, unsig
 template <typename PT, bool SOA, typename MT>
 __global__ void __launch_bounds__(256)
 route_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
-                     const MT *__restrict__ mass, long long np, double scale, int N, int ppr,
-                     unsigned long long *__restrict__ cursor, PT *__restrict__ out_pos, MT *__restrict__ out_mass) {
+                     const MT *__restrict__ mass, long long np, double scale, int N, int ppr, int self,
+                     unsigned long long *__restrict__ cursor, long long capacity, PT *__restrict__ out_pos,
+                     MT *__restrict__ out_mass) {
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long np_pad = (np + 31) & ~31LL;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += stride) {
-        const int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
+        int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
+        if (d == self) d = -1;
+        if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;
         int head, offset, length;
         warp_runs_r(d, lane, head, offset, length);
         unsigned long long slot = 0;
         if (d >= 0 && offset == 0) slot = atomicAdd(cursor + d, (unsigned long long)length);
         slot = __shfl_sync(0xffffffffu, slot, head) + offset;
-        if (d >= 0) {
+        if (d >= 0 && (long long)slot < capacity) {
             PT x, y, z;
             if (SOA) { x = p0[p]; y = p1[p]; z = p2[p]; }
             else     { x = p0[3 * p]; y = p0[3 * p + 1]; z = p0[3 * p + 2]; }
@@ -82,21 +89,22 @@ route_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 
 template <typename PT, bool SOA, typename MT>
 static int route_typed(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass, long long np,
-                       double pos_scale, int nranks, unsigned long long *counts, void *out_pos, void *out_mass,
-                       cudaStream_t st) {
+                       double pos_scale, int nranks, unsigned long long *counts, long long capacity, void *out_pos,
+                       void *out_mass, cudaStream_t st) {
     const int ppr = P->N / nranks;
+    const int self = P->x0 / ppr;
     const double scale = pos_scale * (double)P->N;
     unsigned long long *cursor = counts + nranks;
     APK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * nranks, st));
     if (np > 0) {
         const int blocks = (int)std::min<long long>((np + 255) / 256, (long long)P->num_sms * 16);
-        route_count_kernel<PT, SOA><<<blocks, 256, 0, st>>>((const PT *)p0, np, scale, P->N, ppr, counts);
+        route_count_kernel<PT, SOA><<<blocks, 256, 0, st>>>((const PT *)p0, np, scale, P->N, ppr, self, counts);
         APK_CUDA(cudaGetLastError());
         route_scan_kernel<<<1, 32, 0, st>>>(counts, nranks, cursor);
         APK_CUDA(cudaGetLastError());
         route_scatter_kernel<PT, SOA, MT><<<blocks, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2,
-                                                                  (const MT *)mass, np, scale, P->N, ppr, cursor,
-                                                                  (PT *)out_pos, (MT *)out_mass);
+                                                                  (const MT *)mass, np, scale, P->N, ppr, self, cursor,
+                                                                  capacity, (PT *)out_pos, (MT *)out_mass);
         APK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -104,15 +112,16 @@ static int route_typed(apk_plan *P, const void *p0, const void *p1, const void *
 
 int route_launch(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
                  double pos_scale, const void *mass, int mass_dtype, long long np, int nranks,
-                 unsigned long long *counts, void *out_pos, void *out_mass, cudaStream_t st) {
+                 unsigned long long *counts, long long capacity, void *out_pos, void *out_mass, cudaStream_t st) {
     APK_REQUIRE(nranks >= 1 && nranks <= 1024 && P->N % nranks == 0, "apk_route_particles: nmesh %d not divisible by %d ranks", P->N, nranks);
+    APK_REQUIRE(P->n0 == P->N / nranks && P->x0 % P->n0 == 0, "apk_route_particles: plan slab [%d,%d) is not rank-aligned for %d ranks", P->x0, P->x0 + P->n0, nranks);
     APK_REQUIRE(!mass || mass_dtype == pos_dtype, "apk_route_particles: mass must have the dtype of the positions");
     const bool soa = layout == APK_SOA;
     if (pos_dtype == APK_F32)
-        return soa ? route_typed<float, true, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st)
-                   : route_typed<float, false, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st);
-    return soa ? route_typed<double, true, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st)
-               : route_typed<double, false, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, out_pos, out_mass, st);
+        return soa ? route_typed<float, true, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st)
+                   : route_typed<float, false, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st);
+    return soa ? route_typed<double, true, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st)
+               : route_typed<double, false, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st);
 }
 
 __global__ void __launch_bounds__(256) accumulate_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n) {

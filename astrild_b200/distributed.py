@@ -45,26 +45,36 @@ class CudaSlabBackend:
 
     # -- 1. routing -----------------------------------------------------------------------
     def route(self, pos, mass, pos_scale: float):
+        """Particles of this rank that belong to another slab, grouped by destination:
+        (positions (n,3), masses or None, per-destination counts).  Everything else stays put."""
         eng = self.eng
         p0, p1, p2, layout, dt, npart, keep = eng._positions(pos)
         m = None
         if mass is not None:
             m = eng._to_device(mass).to(dt).contiguous()
-        out_pos = torch.empty((npart, 3), dtype=dt, device=self.device)
-        out_mass = torch.empty(npart, dtype=dt, device=self.device) if m is not None else None
         code = _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64
-        _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),
-                  _ptr(m), code, int(npart), self.nranks, _ptr(self._counts), _ptr(out_pos), _ptr(out_mass), eng.stream)
-        counts = self._counts[: self.nranks].cpu().tolist()
+        capacity = max(1 << 16, npart // 8)
+        while True:
+            out_pos = torch.empty((capacity, 3), dtype=dt, device=self.device)
+            out_mass = torch.empty(capacity, dtype=dt, device=self.device) if m is not None else None
+            _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),
+                      _ptr(m), code, int(npart), self.nranks, _ptr(self._counts), int(capacity), _ptr(out_pos),
+                      _ptr(out_mass), eng.stream)
+            counts = self._counts[: self.nranks].cpu().tolist()
+            total = int(sum(counts))
+            if total <= capacity:
+                break
+            capacity = total                      # rare: more than 1/8 of the particles change slab
         del keep
-        return out_pos, out_mass, counts
+        return out_pos[:total], (None if out_mass is None else out_mass[:total]), counts
 
     def empty_like_rows(self, like: torch.Tensor, rows: int) -> torch.Tensor:
         return torch.empty((rows,) + tuple(like.shape[1:]), dtype=like.dtype, device=self.device)
 
     # -- 2./3. deposit and ghost planes ---------------------------------------------------------
-    def deposit(self, pos_aos, mass, resampler: str, shift: float, pos_scale: float):
-        return self.eng.deposit(pos_aos, mass, resampler, shift, pos_scale, "auto")
+    def deposit(self, pos_aos, mass, resampler: str, shift: float, pos_scale: float, out=None):
+        """Deposit into the slab buffer (with ghost planes); out != None accumulates into it."""
+        return self.eng.deposit(pos_aos, mass, resampler, shift, pos_scale, "auto", out=out, zero=out is None)
 
     def accumulate(self, dst: torch.Tensor, src: torch.Tensor) -> None:
         assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
@@ -174,6 +184,7 @@ class SlabPk:
         self.backend = backend
         self.eng = getattr(backend, "eng", None)
         self.ghost_lo, self.ghost_hi = 1, 2
+        self.profile, self.last_profile = False, {}
         if self.P > 1 and self.n0 < 2:
             raise AstrildPkError("each rank needs at least 2 mesh planes")
 
@@ -218,35 +229,61 @@ class SlabPk:
         """
         be, P = self.backend, self.P
         ps = 1.0 / self.L if pos_scale is None else float(pos_scale)
-        # 1. route
-        if routed or P == 1:
-            rp, rm = pos, mass
-        else:
+        marks = []
+
+        def mark(name):
+            if self.profile and torch.cuda.is_available():
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
+        # 1. route: only particles that change slab travel; the slab deposit ignores particles it
+        #    does not own, so the caller's arrays are deposited as they are
+        parts = [(pos, mass)]
+        if not (routed or P == 1):
             sp, sm, counts = be.route(pos, mass, ps)
-            rp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
-            rm = self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows)) if sm is not None else None
-            del sp, sm
+            mark("route")
+            fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
+            fm = self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows)) if sm is not None else None
+            if fp.shape[0]:
+                parts.append((fp, fm))
+            mark("exchange_particles")
         # 2./3. deposit + ghosts
         shifts = (0.0, 0.5) if self.interlaced else (0.0,)
         owned = []
         for sh in shifts:
-            mesh = be.deposit(rp, rm, self.resampler, sh, ps)
+            mesh = None
+            for rp, rm in parts:
+                mesh = be.deposit(rp, rm, self.resampler, sh, ps, out=mesh)
+            mark("deposit")
             owned.append(self._exchange_ghosts(mesh))
+            mark("ghosts")
         total = be.mesh_sum(owned[0])
         # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
         grids = [be.fft2d(o) for o in owned]
+        mark("fft2d")
         grids = self._transpose(grids)
         del owned
+        mark("transpose")
         grids = [be.fft1d(g, self.ny) for g in grids]
+        mark("fft1d")
         # 7. binning on the transposed slab
         comp = (self.resampler, self.interlaced) if self.compensated else None
         binning = be.make_binning(self.y0, self.ny, kmin, dk, kmax, comp, self.interlaced)
         raw = be.bin(binning, grids[0], grids[1] if self.interlaced else None)
+        mark("bin")
         # 8. reduce
         red = be.to_reduce_tensor(raw, total)
         if P > 1:
             red = self.comm.all_reduce_sum(red)
         host = red.cpu().numpy()
+        mark("reduce")
+        if marks:
+            prof: dict = {}
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                prof[name] = prof.get(name, 0.0) + e0.elapsed_time(e1)
+            self.last_profile = prof
         nb1 = (len(host) - 1) // 4
         ksum, pre, pim = host[:nb1], host[nb1:2 * nb1], host[2 * nb1:3 * nb1]
         nsum = np.rint(host[3 * nb1:4 * nb1]).astype(np.int64)

@@ -249,6 +249,7 @@ def run_ours(args, wl_key: str) -> None:
             return runner.power(tuple(host_pos), pos_scale=1.0, kmin=kmin, normalize=True)
         eng = runner.eng
         binning = None
+        runner.profile = True
     else:
         if wl["kind"] == "zeldovich":
             pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev)
@@ -318,6 +319,7 @@ def run_ours(args, wl_key: str) -> None:
     barrier()
     clocks = sampler.stop()
     ms = t_start.elapsed_time(t_end)
+    slab_profile = dict(runner.last_profile) if world > 1 else None
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -416,7 +418,8 @@ def run_ours(args, wl_key: str) -> None:
            "gpu_launches": (kernels_per_step * args.steps) if kernels_per_step else None,
            "gpu_launches_note": "hand-written kernels per step: brick count + scan + scatter + deposit per mesh, bin + fold; "
                                 "cuFFT launches are library kernels and not counted",
-           "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+           "roofline": roofline, "stages": stages if world == 1 else {"ms_rank0_last_step": {k: round(v, 3) for k, v in slab_profile.items()}},
+           "cpu_baseline": cpu,
            "check": {"first_bins_P": [float(x) for x in res["power"].real[:3]], "modes0": int(res["modes"][0])}}
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -78,22 +78,27 @@ int apk_binning_last_ms(apk_binning *binning, float ms[2]);
  * APK_SOA: p0,p1,p2 -> x,y,z.  mass may be NULL (unit mass).  shift = 0.5 paints the
  * interlaced twin.  zero_first != 0 clears the mesh before accumulating.
  * Slab plans (n0 < N): `mesh` has n_lo + n0 + n_hi planes (apk_plan_ghost_planes), plane 0 is
- * global plane x0 - n_lo; every particle must have floor(g_x - shift) in [x0, x0+n0).
+ * global plane x0 - n_lo; particles whose floor(g_x - shift) is outside [x0, x0+n0) are IGNORED
+ * (their owner deposits them, see apk_route_particles).
  * Single-GPU plans wrap periodically.                                                        */
 int apk_deposit(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
                 int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
                 int resampler, double shift, int method, int zero_first, float *mesh, void *stream);
 
 /* ---- slab routing (multi-GPU) ---------------------------------------------------------------- */
-/* Orders the particles by destination rank = owner of the x-slab holding floor(pos_x*pos_scale*N)
- * (N/nranks planes per rank, N divisible by nranks).  Writes positions as AoS (np,3) of the input
- * dtype into out_pos (and masses, same dtype, into out_mass when mass != NULL) grouped by
- * destination, and the per-destination counts into counts_dev[0..nranks) (uint64; the array must
- * hold 2*nranks entries, the second half is scratch).  The host reads the counts to size the
- * all-to-all.  pmesh equivalent: ParticleMesh.decompose + layout.exchange (unused by astrild).   */
+/* Extracts the particles that must LEAVE this rank: destination = owner of the x-slab holding
+ * floor(pos_x*pos_scale*N) (N/nranks planes per rank).  Particles that stay are not touched -- a
+ * slab plan's apk_deposit ignores particles it does not own, so the caller deposits its original
+ * arrays plus whatever it receives.  Leavers are written as AoS (n,3) of the input dtype into
+ * out_pos (masses, same dtype, into out_mass when mass != NULL), grouped by destination rank;
+ * counts_dev[0..nranks) receives the per-destination counts (uint64, own rank = 0; the array must
+ * hold 2*nranks entries, the second half is scratch).  At most `capacity` particles are written:
+ * the host compares sum(counts) with capacity and retries with a larger buffer if needed.
+ * pmesh equivalent: ParticleMesh.decompose + layout.exchange (unused by astrild).               */
 int apk_route_particles(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
                         int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
-                        int nranks, uint64_t *counts_dev, void *out_pos, void *out_mass, void *stream);
+                        int nranks, uint64_t *counts_dev, int64_t capacity, void *out_pos, void *out_mass,
+                        void *stream);
 /* dst[i] += src[i], i < n: adds received ghost planes into the owned slab                       */
 int apk_mesh_accumulate(apk_plan *plan, float *dst, const float *src, int64_t n, void *stream);
 

@@ -29,28 +29,39 @@ class NumpySlabBackend:
         self.N, self.L, self.x0, self.n0, self.nranks = N, L, x0, n0, nranks
         self.Nk = N // 2 + 1
 
+    def _dest(self, pos, pos_scale):
+        g = np.floor(np.asarray(pos, dtype=np.float64)[:, 0] * (pos_scale * self.N)).astype(np.int64) % self.N
+        return g // (self.N // self.nranks)
+
     def route(self, pos, mass, pos_scale):
         p = np.asarray(pos, dtype=np.float64)
-        g = np.floor(p[:, 0] * (pos_scale * self.N)).astype(np.int64) % self.N
-        dest = g // (self.N // self.nranks)
-        order = np.argsort(dest, kind="stable")
-        counts = np.bincount(dest, minlength=self.nranks).tolist()
+        dest = self._dest(p, pos_scale)
+        me = self.x0 // self.n0
+        leave = np.flatnonzero(dest != me)
+        order = leave[np.argsort(dest[leave], kind="stable")]
+        counts = np.bincount(dest[leave], minlength=self.nranks).tolist()
         sm = None if mass is None else torch.from_numpy(np.asarray(mass, dtype=np.float64)[order].copy())
         return torch.from_numpy(p[order].copy()), sm, counts
 
     def empty_like_rows(self, like, rows):
         return torch.empty((rows,) + tuple(like.shape[1:]), dtype=like.dtype)
 
-    def deposit(self, pos, mass, resampler, shift, pos_scale):
+    def deposit(self, pos, mass, resampler, shift, pos_scale, out=None):
         N = self.N
+        pos = torch.as_tensor(np.asarray(pos, dtype=np.float64))
+        mass = None if mass is None else torch.as_tensor(np.asarray(mass, dtype=np.float64))
+        mine = self._dest(pos.numpy(), pos_scale) == self.x0 // self.n0        # a slab deposit ignores foreign particles
+        pos = pos[torch.from_numpy(mine)]
+        mass = None if mass is None else mass[torch.from_numpy(mine)]
         full = o.paint(pos.numpy() * (pos_scale * self.L), 1.0 if mass is None else mass.numpy(), N, self.L,
                        resampler, shift)
         if self.nranks == 1:
-            return torch.from_numpy(full)
+            return torch.from_numpy(full) if out is None else out.add_(torch.from_numpy(full))
         planes = (np.arange(self.x0 - 1, self.x0 + self.n0 + 2)) % N
         others = np.setdiff1d(np.arange(N), planes)
         assert not full[others].any(), "a routed particle touched a plane outside slab + ghosts"
-        return torch.from_numpy(full[planes].copy())
+        slab = torch.from_numpy(full[planes].copy())
+        return slab if out is None else out.add_(slab)
 
     def accumulate(self, dst, src):
         dst += src
