@@ -363,7 +363,7 @@ int apk_binning_create(apk_binning **out, apk_plan *P, int n_a, int n_b, int nz,
     B->wz = df;
     if (has_comp) { B->icomp2_a = df + nz; B->icomp2_b = B->icomp2_a + n_a; B->icomp2_z = B->icomp2_b + n_b; }
 
-    B->partial_ctas = P->num_sms * 4;
+    B->partial_ctas = P->num_sms * 3;   // = resident CTAs (80 regs, 51 KB smem)
     const size_t pbytes = sizeof(double) * 4 * (size_t)B->partial_ctas * (nedges + 1);
     if (cudaMalloc(&B->partial, pbytes) != cudaSuccess) {
         cudaFree(B->tables); delete B; set_error("apk_binning_create: cudaMalloc(%zu) failed", pbytes); return 1;

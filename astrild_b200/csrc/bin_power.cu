@@ -24,7 +24,6 @@
 namespace apk {
 
 constexpr int BIN_THREADS = 256;
-constexpr int BIN_TA = 4;   // a-rows per work item
 constexpr int BIN_W = 8;    // window slots per thread (power of two)
 
 struct BinArgs {
@@ -53,9 +52,14 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *addr, unsigned l
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
 }
 
+// a-rows per work item: 4 for one grid, 2 when 2-4 grids are read per mode (register budget)
+template <bool INTERLACED, bool CROSS>
+struct BinRows { static constexpr int TA = (INTERLACED || CROSS) ? 2 : 4; };
+
 template <bool INTERLACED, bool CROSS, bool COMP>
-__global__ void __launch_bounds__(BIN_THREADS)
+__global__ void __launch_bounds__(BIN_THREADS, 3)
 bin_power_kernel(BinArgs A) {
+    constexpr int BIN_TA = BinRows<INTERLACED, CROSS>::TA;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: edges2[nedges] | ps[W][T] | ks[W][T] | meta[W][T]
     double *s_e2 = reinterpret_cast<double *>(smem_raw);
@@ -122,8 +126,17 @@ bin_power_kernel(BinArgs A) {
             base[t] = ((size_t)iac * A.n_b) * A.nz + izc;
         }
 
+        bool dc_row[BIN_TA];
+#pragma unroll
+        for (int t = 0; t < BIN_TA; ++t) dc_row[t] = iz == 0 && ia0 + t == A.dc_a;
         float2 v1[BIN_TA], v1s[BIN_TA], v2[BIN_TA], v2s[BIN_TA];
+        double n_kb2 = 0.0;                      // b-row tables travel with the prefetched row
+        float n_icb = 1.f;
+        float2 n_phb = make_float2(1.f, 0.f);
         auto load_row = [&](int ib) {
+            n_kb2 = A.kb2[ib];
+            if (COMP) n_icb = A.ic_b[ib];
+            if (INTERLACED) n_phb = A.ph_b[ib];
 #pragma unroll
             for (int t = 0; t < BIN_TA; ++t) {
                 const size_t idx = base[t] + (size_t)ib * A.nz;
@@ -145,13 +158,10 @@ bin_power_kernel(BinArgs A) {
                 if (INTERLACED) c1s[t] = v1s[t];
                 if (CROSS) { c2[t] = v2[t]; if (INTERLACED) c2s[t] = v2s[t]; }
             }
+            const double kb2 = n_kb2;
+            const float icb = n_icb;
+            const float2 phb = n_phb;
             if (ib + 1 < ib1) load_row(ib + 1);   // software prefetch of the next b-row
-
-            const double kb2 = A.kb2[ib];
-            float icb = 1.f;
-            float2 phb = make_float2(1.f, 0.f);
-            if (COMP) icb = A.ic_b[ib];
-            if (INTERLACED) phb = A.ph_b[ib];
 
 #pragma unroll
             for (int t = 0; t < BIN_TA; ++t) {
@@ -161,7 +171,13 @@ bin_power_kernel(BinArgs A) {
                 if (k2 >= e2_last) { over_cnt += wi; continue; }
                 if (k2 < e2_first) { under_cnt += wi; continue; }
                 // --- bin: float guess, exact float64 fix-up against kedges^2 -----------------
-                int bin = (int)((sqrtf((float)k2) - A.kmin_f) * A.inv_dk_f) + 1;
+                // sqrt(k2): float rsqrt seed + one Newton step in float64 (rel. error ~1e-14)
+                const float k2f = (float)k2;
+                const float rs = k2f > 0.f ? rsqrtf(k2f) : 0.f;
+                const double y = (double)rs;
+                double kk = k2 * y;
+                kk = fma(0.5 * y, fma(-kk, kk, k2), kk);
+                int bin = (int)((k2f * rs - A.kmin_f) * A.inv_dk_f) + 1;
                 bin = max(1, min(bin, nedges - 1));
                 while (k2 < s_e2[bin - 1]) --bin;
                 while (k2 >= s_e2[bin]) ++bin;
@@ -187,7 +203,7 @@ bin_power_kernel(BinArgs A) {
                     pim = 0.f;
                 }
                 if (COMP) { const float ic = ica[t] * icb; pre *= ic; pim *= ic; }
-                if (iz == 0 && ib == A.dc_b && ia0 + t == A.dc_a) { pre = 0.f; pim = 0.f; }
+                if (dc_row[t] && ib == A.dc_b) { pre = 0.f; pim = 0.f; }
                 const double w = (double)wi;
                 if (CROSS && singular && pim != 0.f) red_add_f64(g_pim + bin, (double)pim);
                 // --- private window update ---------------------------------------------------
@@ -210,7 +226,7 @@ bin_power_kernel(BinArgs A) {
                 m.y += (int)wi;
                 s_meta[slot] = m;
                 s_ps[slot] = fma(w, (double)pre, ps);
-                s_ks[slot] = fma(w, sqrt(k2), ks);
+                s_ks[slot] = fma(w, kk, ks);
             }
         }
     }
@@ -300,7 +316,8 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
 
     const int ctas = B->partial_ctas;
     const int nb1 = B->nedges + 1;
-    A.n_ga = (B->n_a + BIN_TA - 1) / BIN_TA;
+    const int ta = (interlaced || cross) ? 2 : 4;      // BinRows<>::TA
+    A.n_ga = (B->n_a + ta - 1) / ta;
     A.n_zc = (B->nz + 31) / 32;
     // choose the b-segment so that there are several work items per warp
     const long long warps = (long long)ctas * (BIN_THREADS / 32);
