@@ -36,8 +36,12 @@
 
 namespace apk {
 
-constexpr int BX = 12, BY = 12, BZ = 32;        // brick edge in cells (x, y multiples of 3; z = warp)
-constexpr int BRICK_CELLS = BX * BY * BZ;       // 4608
+constexpr int BX = 12, BY = 12;                 // brick edge in cells along x, y (multiples of 3)
+constexpr int BZ = 32;                          // z-lanes of a column = tile cells along z (one warp)
+// home cells along z: 32 - (S-1), so that a column's 32 lanes are exactly its 32 tile cells
+// (30 home cells + 2 halo lanes for TSC, 31 + 1 for CIC) and the spread needs no halo special case
+template <int S> struct BrickZ { static constexpr int CELLS = BZ - (S - 1); };
+constexpr int BRICK_CELLS = BX * BY * BZ;       // 4608 count slots (halo lanes stay empty)
 constexpr int DEP_THREADS = 512;                // 16 warps = 16 columns of one colour class
 constexpr int CH = 5120;                        // particles per shared-memory chunk
 constexpr int PPT = CH / DEP_THREADS;           // particles per thread per chunk
@@ -50,11 +54,12 @@ struct BrickGrid {
     int nbricks;
 };
 
-static BrickGrid make_brick_grid(const DepositGeom &G) {
+static BrickGrid make_brick_grid(const DepositGeom &G, int S) {
     BrickGrid B;
+    const int bzc = BZ - (S - 1);
     B.nbx = (G.nplanes + BX - 1) / BX;
     B.nby = (G.N + BY - 1) / BY;
-    B.nbz = (G.N + BZ - 1) / BZ;
+    B.nbz = (G.N + bzc - 1) / bzc;
     B.nbricks = B.nbx * B.nby * B.nbz;
     return B;
 }
@@ -102,7 +107,7 @@ __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const Dep
             if (hl < 0) hl += G.N; else if (hl >= G.N) hl -= G.N;
             if (hl >= G.nplanes) hl = 0;                                // unreachable for owned particles
         }
-        const int edge = d == 0 ? BX : (d == 1 ? BY : BZ);
+        const int edge = d == 0 ? BX : (d == 1 ? BY : BrickZ<S>::CELLS);
         b[d] = hl / edge;
         l[d] = frac + (float)(hl - b[d] * edge);
     }
@@ -276,7 +281,7 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 
 template <int S>
 struct TileDims {
-    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ + S - 1;
+    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ;
     static constexpr int SIZE = TX * TY * TZ;
 };
 
@@ -405,8 +410,8 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                     int hx, hy, hz;
                     if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
                     else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
-                    hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BZ - 1));
-                    const int cell = (hx * BY + hy) * BZ + hz;
+                    hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BrickZ<S>::CELLS - 1));
+                    const int cell = (hx * BY + hy) * BZ + hz + OFF;          // z-lane = home z + OFF
                     packed[h * HALF + k] = -1;
                     if (i < nchunk) packed[h * HALF + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
                 }
@@ -471,37 +476,33 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
             for (int cls = 0; cls < 9; ++cls) {
                 const int cx = 3 * (warp >> 2) + cls / 3;
                 const int cy = 3 * (warp & 3) + cls % 3;
-                const int cell = (cx * BY + cy) * BZ + lane;
+                const int cell = (cx * BY + cy) * BZ + lane;              // lane = tile z index = home z + OFF
                 const int beg = cnt[cell], end = cnt[cell + 1];
                 if (__ballot_sync(0xffffffffu, end > beg) != 0u) {
                     Moments<S, MASS> M;
                     M.clear();
-                    const float fx = (float)cx, fy = (float)cy, fz = (float)lane;
+                    const float fx = (float)cx, fy = (float)cy, fz = (float)(lane - OFF);
                     for (int p = beg; p < end; ++p)
                         M.add(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? sm[p] : 1.f);
-                    // z-spread by shuffles: tile z index t = lane + jz.  The lane's own target is
-                    // t = lane + OFF; lane 0 / lane 31 also feed the two z-halo cells (one merged RMW).
-                    float *col = tile + (cx * TD::TY + cy) * TD::TZ + lane + OFF;
-                    const float up_on = lane == 0 ? 0.f : 1.f, dn_on = lane == 31 ? 0.f : 1.f;
-                    // halo cell of this lane (relative to its own target): lane 0 -> t = 0, lane 31 -> t = TZ-1
-                    const bool halo_lane = (lane == 31) || (S == 3 && lane == 0);
-                    const int halo_off = (lane == 31) ? (TD::TZ - 1) - (31 + OFF) : -OFF;
+                    // z-spread by shuffles.  Every lane owns exactly one tile cell (t = lane): it gets the
+                    // middle weight of its own home cell plus the outer weights of its z-neighbours.  The
+                    // halo lanes (TSC: 0 and 31, CIC: 31) have no home cell, so their moments are zero and
+                    // the shuffles need no edge masks (CIC: lane 0 must drop its wrapped-around 'up').
+                    float *col = tile + (cx * TD::TY + cy) * TD::TZ + lane;
+                    const float up_on = (S == 2 && lane == 0) ? 0.f : 1.f;
 #pragma unroll
                     for (int a = 0; a < S; ++a)
 #pragma unroll
                         for (int b = 0; b < S; ++b) {
-                            const float hi = M.get(a, b, S - 1), lo = M.get(a, b, 0);
-                            const float up = __shfl_up_sync(0xffffffffu, hi, 1);
+                            const float up = __shfl_up_sync(0xffffffffu, M.get(a, b, S - 1), 1);
                             float own;
                             if (S == 2) {
-                                own = fmaf(up, up_on, lo);
+                                own = fmaf(up, up_on, M.get(a, b, 0));
                             } else {
-                                const float dn = __shfl_down_sync(0xffffffffu, lo, 1);
-                                own = fmaf(up, up_on, fmaf(dn, dn_on, M.get(a, b, S / 2)));
+                                const float dn = __shfl_down_sync(0xffffffffu, M.get(a, b, 0), 1);
+                                own = M.get(a, b, S / 2) + up + dn;
                             }
-                            float *cell_ptr = col + (a * TD::TY + b) * TD::TZ;
-                            *cell_ptr += own;
-                            if (halo_lane) cell_ptr[halo_off] += (lane == 31) ? hi : lo;
+                            col[(a * TD::TY + b) * TD::TZ] += own;
                         }
                 }
                 __syncthreads();
@@ -512,7 +513,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
         const int bz = brick % B.nbz;
         const int by = (brick / B.nbz) % B.nby;
         const int bx = brick / (B.nbz * B.nby);
-        const int gz0 = bz * BZ - OFF;                     // global z of tile index 0
+        const int gz0 = bz * BrickZ<S>::CELLS - OFF;       // global z of tile index 0
         const bool fast_z = gz0 >= 0 && gz0 + TD::TZ <= G.N && (G.N & 1) == 0;
         // rows of this warp: r = warp + 16 j; lane j prepares row j's mesh offset (-1: skip)
         constexpr int ROWS = TD::TX * TD::TY, WARPS = DEP_THREADS / 32;
@@ -535,16 +536,17 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
             float *grow = mesh + off;
             const float *trow = tile + (warp + WARPS * j) * TD::TZ;
             if (fast_z) {
-                // pairs start at tile index OFF (global z even); index 0 (TSC) and TZ-1 are single cells
-                if (lane < BZ / 2) {
-                    const float v0 = trow[OFF + 2 * lane], v1 = trow[OFF + 2 * lane + 1];
-                    if (v0 != 0.f || v1 != 0.f) red_add_v2(grow + gz0 + OFF + 2 * lane, v0, v1);
-                } else if (lane == BZ / 2) {
-                    const float v = trow[TD::TZ - 1];
-                    if (v != 0.f) atomicAdd(grow + gz0 + TD::TZ - 1, v);
-                } else if (S == 3 && lane == BZ / 2 + 1) {
-                    const float v = trow[0];
-                    if (v != 0.f) atomicAdd(grow + gz0, v);
+                // aligned pairs (global z even) go out as RED.ADD.V2.F32; if the row starts on an odd z its
+                // first and last cells are single
+                const int first = gz0 & 1;
+                if (lane < 16 - first) {
+                    const int t = first + 2 * lane;
+                    const float v0 = trow[t], v1 = trow[t + 1];
+                    if (v0 != 0.f || v1 != 0.f) red_add_v2(grow + gz0 + t, v0, v1);
+                } else if (first && lane >= 30) {
+                    const int t = lane == 30 ? 0 : 31;
+                    const float v = trow[t];
+                    if (v != 0.f) atomicAdd(grow + gz0 + t, v);
                 }
             } else {
                 for (int tz = lane; tz < TD::TZ; tz += 32) {
@@ -557,7 +559,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
 }
 
 static size_t max_bricks(const apk_plan *P) {
-    return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + BZ - 1) / BZ);
+    return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + 29) / 30);
 }
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -571,7 +573,7 @@ template <int S, typename PT, bool SOA, bool MASS>
 static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass,
                       int mass_dtype, long long np, const DepositGeom &G, float *mesh, cudaStream_t st) {
     using VT = typename std::conditional<MASS, P4, P3>::type;
-    const BrickGrid B = make_brick_grid(G);
+    const BrickGrid B = make_brick_grid(G, S);
     const size_t need = deposit_sorted_workspace_bytes(P, np, MASS);
     APK_REQUIRE(P->workspace && P->workspace_bytes >= need,
                 "apk_deposit: sorted path needs %zu workspace bytes, %zu set (apk_plan_workspace_bytes / apk_plan_set_workspace)",
