@@ -150,11 +150,10 @@ class CatalogMesh:
 
     def _complex_fields(self):
         eng, a = self._eng, self.attrs
-        mesh = eng.deposit(self._pos, self._w, a["resampler"], 0.0, self._pos_scale, self._method)
+        shifts = (0.0, 0.5) if a["interlaced"] else (0.0,)
+        meshes = eng.deposit_many(self._pos, self._w, a["resampler"], shifts, self._pos_scale, self._method)
+        mesh, mesh_s = meshes[0], (meshes[1] if a["interlaced"] else None)
         total = eng.mesh_sum(mesh) if self._normalize else None
-        mesh_s = None
-        if a["interlaced"]:
-            mesh_s = eng.deposit(self._pos, self._w, a["resampler"], 0.5, self._pos_scale, self._method)
         if self._normalize:
             scale = eng.N ** 3 / total
         else:
