@@ -32,7 +32,7 @@ SIGNATURES = {
     "apk_plan_create": [ct.POINTER(_vp), _i, _d, _i, _i, _i],
     "apk_plan_destroy": [_vp],
     "apk_plan_mesh_elems": [_vp, ct.POINTER(_i64)],
-    "apk_plan_workspace_bytes": [_vp, _i64, _i, ct.POINTER(_sz)],
+    "apk_plan_workspace_bytes": [_vp, _i64, _i, _i, ct.POINTER(_sz)],
     "apk_plan_set_workspace": [_vp, _vp, _sz],
     "apk_plan_ghost_planes": [_vp, ct.POINTER(_i), ct.POINTER(_i)],
     "apk_plan_enable_timing": [_vp, _i],
@@ -41,6 +41,7 @@ SIGNATURES = {
     "apk_deposit": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _d, _i, _i, _vp, _vp],
     "apk_route_particles": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp],
     "apk_mesh_accumulate": [_vp, _vp, _vp, _i64, _vp],
+    "apk_deposit_interlaced": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp],
     "apk_mesh_sum": [_vp, _vp, _i, _vp, _vp],
     "apk_padded_mesh_sum": [_vp, _vp, _vp, _vp],
     "apk_load_mesh": [_vp, _vp, _i, _d, _vp, _vp],

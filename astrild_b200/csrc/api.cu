@@ -21,8 +21,8 @@ void set_error(const char *fmt, ...) {
 int deposit_atomic_launch(const void *, const void *, const void *, int, int, const void *, int, long long,
                           int, const DepositGeom &, float *, int, cudaStream_t);
 int deposit_sorted_launch(apk_plan *, const void *, const void *, const void *, int, int, const void *, int,
-                          long long, int, const DepositGeom &, float *, cudaStream_t);
-size_t deposit_sorted_workspace_bytes(const apk_plan *, long long np, int with_mass);
+                          long long, int, const DepositGeom &, float *, float *, cudaStream_t);
+size_t deposit_sorted_workspace_bytes(const apk_plan *, long long np, int with_mass, int pair);
 int mesh_sum_launch(apk_plan *, const void *, int, double *, cudaStream_t);
 int padded_mesh_sum_launch(apk_plan *, const float *, double *, cudaStream_t);
 int load_mesh_launch(apk_plan *, const void *, int, double, float *, cudaStream_t);
@@ -137,9 +137,9 @@ int apk_plan_ghost_planes(const apk_plan *P, int *n_lo, int *n_hi) {
     return 0;
 }
 
-int apk_plan_workspace_bytes(const apk_plan *P, int64_t max_particles, int with_mass, size_t *bytes) {
+int apk_plan_workspace_bytes(const apk_plan *P, int64_t max_particles, int with_mass, int interlaced, size_t *bytes) {
     APK_REQUIRE(P && bytes, "apk_plan_workspace_bytes: null argument");
-    size_t dep = deposit_sorted_workspace_bytes(P, max_particles, with_mass);
+    size_t dep = deposit_sorted_workspace_bytes(P, max_particles, with_mass, interlaced);
     size_t fft = P->fft_work_bytes;
     *bytes = (dep > fft ? dep : fft) + 256;
     return 0;
@@ -152,9 +152,9 @@ int apk_plan_set_workspace(apk_plan *P, void *workspace, size_t bytes) {
     return 0;
 }
 
-int apk_deposit(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
-                double pos_scale, const void *mass, int mass_dtype, int64_t np, int resampler,
-                double shift, int method, int zero_first, float *mesh, void *stream) {
+static int deposit_impl(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
+                        double pos_scale, const void *mass, int mass_dtype, int64_t np, int resampler,
+                        double shift, int method, int zero_first, float *mesh, float *mesh1, void *stream) {
     APK_REQUIRE(P && mesh, "apk_deposit: null plan or mesh");
     APK_REQUIRE(np >= 0, "apk_deposit: negative particle count");
     APK_REQUIRE(np == 0 || p0, "apk_deposit: null positions");
@@ -163,24 +163,56 @@ int apk_deposit(apk_plan *P, const void *p0, const void *p1, const void *p2, int
     APK_REQUIRE(resampler >= APK_NGP && resampler <= APK_TSC, "apk_deposit: bad resampler %d", resampler);
     DeviceGuard guard(P->device);
     cudaStream_t st = (cudaStream_t)stream;
-    DepositGeom G;
-    G.N = P->N; G.ldz = P->ldz; G.scale = pos_scale * (double)P->N; G.shift = shift;
-    G.slab = P->n0 < P->N; G.plane0 = P->x0 - P->ghost_lo; G.nplanes = P->ghost_lo + P->n0 + P->ghost_hi;
-    G.own0 = P->x0; G.nown = P->n0;
-    if (zero_first)
-        APK_CUDA(cudaMemsetAsync(mesh, 0, sizeof(float) * (size_t)G.nplanes * P->N * P->ldz, st));
+    auto geom = [&](double sh) {
+        DepositGeom G;
+        G.N = P->N; G.ldz = P->ldz; G.scale = pos_scale * (double)P->N; G.shift = sh;
+        G.slab = P->n0 < P->N; G.plane0 = P->x0 - P->ghost_lo; G.nplanes = P->ghost_lo + P->n0 + P->ghost_hi;
+        G.own0 = P->x0; G.nown = P->n0;
+        G.s0 = (float)G.scale;
+        G.s1 = (float)(G.scale - (double)G.s0);
+        G.s2 = (float)(G.scale - (double)G.s0 - (double)G.s1);
+        G.t32 = -1.f;
+        if ((sh == 0.0 || sh == 0.5) && fabs(G.scale) < 1e30 && fabs(G.scale) > 1e-30)
+            G.t32 = (float)sh + (resampler == APK_CIC ? 0.f : 0.5f);
+        return G;
+    };
+    const DepositGeom G = geom(shift);
+    const size_t mesh_bytes = sizeof(float) * (size_t)G.nplanes * P->N * P->ldz;
+    if (zero_first) {
+        APK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, st));
+        if (mesh1) APK_CUDA(cudaMemsetAsync(mesh1, 0, mesh_bytes, st));
+    }
     if (method == APK_DEPOSIT_AUTO)
         method = (np >= (1 << 18)) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
     P->dep_timed = false;
     if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
-        return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, st);
+        return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
     if (P->mark(3, st)) { set_error("apk_deposit: event record failed"); return 1; }
     int rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
     if (rc) return rc;
+    if (mesh1) {
+        rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, geom(shift + 0.5), mesh1, P->num_sms, st);
+        if (rc) return rc;
+    }
     if (P->mark(4, st)) { set_error("apk_deposit: event record failed"); return 1; }
     P->dep_timed = P->timing;
     P->dep_sorted = false;
     return 0;
+}
+
+int apk_deposit(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
+                double pos_scale, const void *mass, int mass_dtype, int64_t np, int resampler,
+                double shift, int method, int zero_first, float *mesh, void *stream) {
+    return deposit_impl(P, p0, p1, p2, layout, pos_dtype, pos_scale, mass, mass_dtype, np, resampler, shift, method,
+                        zero_first, mesh, nullptr, stream);
+}
+
+int apk_deposit_interlaced(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
+                           double pos_scale, const void *mass, int mass_dtype, int64_t np, int resampler,
+                           int method, int zero_first, float *mesh, float *mesh_shifted, void *stream) {
+    APK_REQUIRE(mesh_shifted, "apk_deposit_interlaced: null shifted mesh");
+    return deposit_impl(P, p0, p1, p2, layout, pos_dtype, pos_scale, mass, mass_dtype, np, resampler, 0.0, method,
+                        zero_first, mesh, mesh_shifted, stream);
 }
 
 int apk_plan_enable_timing(apk_plan *P, int on) {

@@ -13,18 +13,31 @@ struct DepositGeom {
     int slab;       // 0: whole periodic mesh, 1: slab with ghost planes
     int plane0;     // global index of local plane 0 (x0 - ghost_lo), may be negative
     int nplanes;    // local planes (ghost_lo + n0 + ghost_hi), == N when !slab
+    float s0, s1, s2;   // scale as an unevaluated sum of three floats (error-free float32 index path)
+    float t32;          // shift + (0.5 for TSC/NGP rounding) when exactly representable, else < 0 (use float64)
     int own0;       // first owned plane x0
     int nown;       // owned planes n0; slab plans deposit only particles with floor(g_x - shift) owned
 
     __host__ __device__ __forceinline__ int local_plane(long long ix) const;
 };
 
-__host__ __device__ __forceinline__ int wrap_index(long long i, int N) {
-    if ((unsigned long long)i < (unsigned long long)N) return (int)i;
-    if (i < 0 && i >= -(long long)N) return (int)(i + N);
-    if (i >= N && i < 2LL * N) return (int)(i - N);
+// far-out-of-box indices: kept out of line so the integer division is never speculated
+__host__ __device__ __noinline__ static int wrap_index_slow(long long i, int N) {
     long long r = i % N;
     return (int)(r < 0 ? r + N : r);
+}
+
+// periodic wrap of a cell index; positions within one box length of the box take the fast path
+__host__ __device__ __forceinline__ int wrap_index(long long i, int N) {
+    if (i < 0) i += N; else if (i >= N) i -= N;
+    if ((unsigned long long)i >= (unsigned long long)N) return wrap_index_slow(i, N);
+    return (int)i;
+}
+
+__host__ __device__ __forceinline__ int wrap_index32(int i, int N) {
+    if (i < 0) i += N; else if (i >= N) i -= N;
+    if ((unsigned)i >= (unsigned)N) return wrap_index_slow((long long)i, N);
+    return i;
 }
 
 __host__ __device__ __forceinline__ int DepositGeom::local_plane(long long ix) const {

@@ -80,14 +80,6 @@ __device__ __forceinline__ double floor_magic(double g, int &i) {
     return rd;
 }
 
-__device__ __forceinline__ int wrap_index32(int i, int N) {
-    if ((unsigned)i < (unsigned)N) return i;
-    if (i < 0 && i >= -N) return i + N;
-    if (i >= N && i < 2 * N) return i - N;
-    const int r = i % N;
-    return r < 0 ? r + N : r;
-}
-
 // brick key and brick-local coordinates of particle p (shared by the count and scatter passes so
 // both see bit-identical keys).  g = x * scale + shift in float64, exactly the oracle's expression.
 template <int S>
@@ -114,42 +106,72 @@ __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const Dep
     return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
 }
 
-// coordinates of the 4 consecutive particles p4 .. p4+3 (clamped to np-1), all loads issued up
-// front; VEC: 128-bit loads (float columns / float AoS, 16-byte aligned bases)
-template <typename PT, bool SOA, bool VEC>
-__device__ __forceinline__ void load4(const PT *__restrict__ p0, const PT *__restrict__ p1,
-                                      const PT *__restrict__ p2, long long p4, long long np, double (&x)[4][3]) {
-    if constexpr (VEC) {
-        if (p4 + 3 < np) {
-            if (SOA) {
-                const float4 a = __ldcs(reinterpret_cast<const float4 *>(p0 + p4));
-                const float4 b = __ldcs(reinterpret_cast<const float4 *>(p1 + p4));
-                const float4 c = __ldcs(reinterpret_cast<const float4 *>(p2 + p4));
-                x[0][0] = a.x; x[1][0] = a.y; x[2][0] = a.z; x[3][0] = a.w;
-                x[0][1] = b.x; x[1][1] = b.y; x[2][1] = b.z; x[3][1] = b.w;
-                x[0][2] = c.x; x[1][2] = c.y; x[2][2] = c.z; x[3][2] = c.w;
-            } else {
-                const float4 a = __ldcs(reinterpret_cast<const float4 *>(p0 + 3 * p4));
-                const float4 b = __ldcs(reinterpret_cast<const float4 *>(p0 + 3 * p4 + 4));
-                const float4 c = __ldcs(reinterpret_cast<const float4 *>(p0 + 3 * p4 + 8));
-                x[0][0] = a.x; x[0][1] = a.y; x[0][2] = a.z; x[1][0] = a.w;
-                x[1][1] = b.x; x[1][2] = b.y; x[2][0] = b.z; x[2][1] = b.w;
-                x[2][2] = c.x; x[3][0] = c.y; x[3][1] = c.z; x[3][2] = c.w;
-            }
-            return;
+// The same for float32 positions without any float64 instruction (the partition kernels are
+// issue-bound and FP64 issues at half rate).  g = x * scale is carried as p + e with
+// p = fl(x*s0) and e = the exact rounding error of p plus x*(s1 + s2): an error-free product good
+// to ~2^-70, so floor() and the in-cell fraction agree with the float64 expression except for
+// products within ~1e-13 of an integer, where the window weights are continuous anyway.
+template <int S>
+__device__ __forceinline__ unsigned int brick_of_f32(const float *x, const DepositGeom &G, const BrickGrid &B,
+                                                     float (&l)[3]) {
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float p = __fmul_rn(x[d], G.s0);      // intrinsics: never contracted into an FMA
+        float e = fmaf(x[d], G.s0, -p);
+        e = fmaf(x[d], G.s1, e);
+        e = fmaf(x[d], G.s2, e);
+        float h = floorf(p);
+        float f = __fadd_rn(__fsub_rn(p, h), e);     // p - h is exact; f in [e, 1 + e)
+        if (d == 0 && G.slab) {                      // ownership: floor of the UNSHIFTED coordinate
+            const int hu = (int)(h + floorf(f));
+            int rel = wrap_index32(hu, G.N) - G.own0;
+            if (rel < 0 || rel >= G.nown) return 0xffffffffu;
         }
+        f += G.t32;                                  // + shift (+ 0.5: TSC rounds to the nearest cell)
+        const float c = floorf(f);
+        h += c;
+        f -= c;                                      // [0, 1)
+        const float frac = (S == 2) ? f : f - 0.5f;  // relative to the home cell
+        int hl = wrap_index32((int)h, G.N);
+        if (d == 0 && G.slab) {
+            hl -= G.plane0;
+            if (hl < 0) hl += G.N; else if (hl >= G.N) hl -= G.N;
+            if (hl >= G.nplanes) hl = 0;
+        }
+        const int edge = d == 0 ? BX : (d == 1 ? BY : BrickZ<S>::CELLS);
+        b[d] = hl / edge;
+        l[d] = frac + (float)(hl - b[d] * edge);
     }
-    PT t[4][3];
+    return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
+}
+
+template <int S, typename PT>
+__device__ __forceinline__ unsigned int brick_of_any(const PT *x, const DepositGeom &G, const BrickGrid &B,
+                                                     float (&l)[3]) {
+    if constexpr (std::is_same<PT, float>::value) {
+        if (G.t32 >= 0.f) return brick_of_f32<S>(x, G, B, l);
+    }
+    const double xd[3] = {(double)x[0], (double)x[1], (double)x[2]};
+    return brick_of<S>(xd, G, B, l);
+}
+
+// raw coordinates of this thread's 4 particles of a tile, v[3*k + d]: slice k of the tile is the
+// PART_THREADS consecutive particles base + k*PART_THREADS + tid, so the 32 lanes of a warp always hold 32
+// CONSECUTIVE particles (long runs of equal brick keys, coalesced 4-byte loads).  All 12 loads are
+// issued up front; indices are clamped to np-1 and masked by the caller.
+template <typename PT> struct Raw4 { PT v[12]; };
+
+template <typename PT, bool SOA>
+__device__ __forceinline__ void load4(const PT *__restrict__ p0, const PT *__restrict__ p1,
+                                      const PT *__restrict__ p2, long long first, int stride, long long np,
+                                      Raw4<PT> &r) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const long long p = min(p4 + k, np - 1);
-        if (SOA) { t[k][0] = p0[p]; t[k][1] = p1[p]; t[k][2] = p2[p]; }
-        else     { t[k][0] = p0[3 * p]; t[k][1] = p0[3 * p + 1]; t[k][2] = p0[3 * p + 2]; }
+        const long long p = min(first + (long long)k * stride, np - 1);
+        if (SOA) { r.v[3 * k] = __ldcs(p0 + p); r.v[3 * k + 1] = __ldcs(p1 + p); r.v[3 * k + 2] = __ldcs(p2 + p); }
+        else     { r.v[3 * k] = __ldcs(p0 + 3 * p); r.v[3 * k + 1] = __ldcs(p0 + 3 * p + 1); r.v[3 * k + 2] = __ldcs(p0 + 3 * p + 2); }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int d = 0; d < 3; ++d) x[k][d] = (double)t[k][d];
 }
 
 // run-length aggregation inside a warp: lanes holding the same key as their left neighbour form a
@@ -169,32 +191,36 @@ __device__ __forceinline__ void warp_runs(unsigned int key, int lane, int &head,
 constexpr int PART_THREADS = 256;
 constexpr int PART_ITEMS = 4;    // consecutive particles per thread per tile
 
-template <int S, typename PT, bool SOA, bool VEC>
+// PAIR: one partition serves the interlaced twins (G: shift 0, G1: shift 0.5).  Every particle is filed
+// under the brick of its mesh-0 home cell; the ~11 % whose mesh-1 home cell lies in a different brick get
+// a second, mesh-1-only copy there (the first copy is then flagged mesh-0-only).
+template <int S, typename PT, bool SOA, bool PAIR>
 __global__ void __launch_bounds__(PART_THREADS)
 brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2, long long np,
-                   DepositGeom G, BrickGrid B, unsigned int *__restrict__ counts) {
+                   DepositGeom G, DepositGeom G1, BrickGrid B, unsigned int *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
-    for (long long base = (long long)blockIdx.x * tile; base < np; base += (long long)gridDim.x * tile) {
-        const long long p4 = base + 4 * threadIdx.x;
-        double x[4][3];
-        load4<PT, SOA, VEC>(p0, p1, p2, p4, np, x);
-        unsigned int key[4];
+    const long long step = (long long)gridDim.x * tile;
+    long long base = (long long)blockIdx.x * tile;
+    Raw4<PT> nxt;
+    if (base < np) load4<PT, SOA>(p0, p1, p2, base + threadIdx.x, PART_THREADS, np, nxt);
+    for (; base < np; base += step) {
+        const long long first = base + threadIdx.x;
+        const Raw4<PT> cur = nxt;
+        if (base + step < np) load4<PT, SOA>(p0, p1, p2, first + step, PART_THREADS, np, nxt);   // next tile in flight
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float l[3];
-            key[k] = brick_of<S>(x[k], G, B, l);
-            if (p4 + k >= np) key[k] = 0xffffffffu;
-        }
-        int head, offset, length;
-        if (__all_sync(0xffffffffu, key[0] == key[1] && key[0] == key[2] && key[0] == key[3] && key[0] != 0xffffffffu)) {
-            warp_runs(key[0], lane, head, offset, length);      // the usual case: one run per thread
-            if (offset == 0) atomicAdd(counts + key[0], 4u * (unsigned int)length);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                warp_runs(key[k], lane, head, offset, length);
-                if (key[k] != 0xffffffffu && offset == 0) atomicAdd(counts + key[k], (unsigned int)length);
+            unsigned int key = brick_of_any<S, PT>(cur.v + 3 * k, G, B, l);
+            if (first + (long long)k * PART_THREADS >= np) key = 0xffffffffu;
+            int head, offset, length;
+            warp_runs(key, lane, head, offset, length);
+            if (key != 0xffffffffu && offset == 0) atomicAdd(counts + key, (unsigned int)length);
+            if constexpr (PAIR) {
+                float l1[3];
+                const unsigned int key1 = brick_of_any<S, PT>(cur.v + 3 * k, G1, B, l1);
+                const bool extra = key != 0xffffffffu && key1 != key;
+                if (__any_sync(0xffffffffu, extra) && extra) atomicAdd(counts + key1, 1u);
             }
         }
     }
@@ -234,46 +260,55 @@ brick_scan_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *
     if (tid == 1023) start[n] = run;
 }
 
-template <int S, typename PT, bool SOA, bool VEC, bool MASS, typename VT>
+// PAIR payload: u + 1 per axis, u = unshifted coordinate relative to the brick origin (>= -1); the sign
+// of x says "not for mesh 0", the sign of y "not for mesh 1".
+template <int S, typename PT, bool SOA, bool MASS, bool PAIR, typename VT>
 __global__ void __launch_bounds__(PART_THREADS)
 brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
-                     const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, BrickGrid B,
-                     unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
+                     const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, DepositGeom G1,
+                     BrickGrid B, unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
-    for (long long base = (long long)blockIdx.x * tile; base < np; base += (long long)gridDim.x * tile) {
-        const long long p4 = base + 4 * threadIdx.x;
-        double x[4][3];
-        load4<PT, SOA, VEC>(p0, p1, p2, p4, np, x);
-        unsigned int key[4];
-        VT v[4];
+    const long long step = (long long)gridDim.x * tile;
+    long long base = (long long)blockIdx.x * tile;
+    Raw4<PT> nxt;
+    if (base < np) load4<PT, SOA>(p0, p1, p2, base + threadIdx.x, PART_THREADS, np, nxt);
+    for (; base < np; base += step) {
+        const long long first = base + threadIdx.x;
+        const Raw4<PT> cur = nxt;
+        if (base + step < np) load4<PT, SOA>(p0, p1, p2, first + step, PART_THREADS, np, nxt);   // next tile in flight
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            const long long p = first + (long long)k * PART_THREADS;
             float l[3];
-            key[k] = brick_of<S>(x[k], G, B, l);
-            v[k].x = l[0]; v[k].y = l[1]; v[k].z = l[2];
-            if (p4 + k >= np) key[k] = 0xffffffffu;
+            unsigned int key = brick_of_any<S, PT>(cur.v + 3 * k, G, B, l);
+            if (p >= np) key = 0xffffffffu;
+            VT v;
+            v.x = l[0]; v.y = l[1]; v.z = l[2];
             if constexpr (MASS) {
-                const long long p = min(p4 + k, np - 1);
-                v[k].m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
+                const long long pc = min(p, np - 1);
+                v.m = mass_f64 ? (float)((const double *)mass)[pc] : ((const float *)mass)[pc];
             }
-        }
-        int head, offset, length;
-        if (__all_sync(0xffffffffu, key[0] == key[1] && key[0] == key[2] && key[0] == key[3] && key[0] != 0xffffffffu)) {
-            warp_runs(key[0], lane, head, offset, length);
+            unsigned int key1 = key;
+            float l1[3];
+            if constexpr (PAIR) {
+                key1 = brick_of_any<S, PT>(cur.v + 3 * k, G1, B, l1);
+                v.x = fmaxf(l[0] + 1.f, 0.f); v.y = fmaxf(l[1] + 1.f, 0.f); v.z = fmaxf(l[2] + 1.f, 0.f);
+                if (key1 != key) v.y = -v.y;                     // first copy is mesh-0-only
+            }
+            int head, offset, length;
+            warp_runs(key, lane, head, offset, length);
             unsigned int slot = 0;
-            if (offset == 0) slot = atomicAdd(cursor + key[0], 4u * (unsigned int)length);
-            slot = __shfl_sync(0xffffffffu, slot, head) + 4u * offset;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) vals[slot + k] = v[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                warp_runs(key[k], lane, head, offset, length);
-                unsigned int slot = 0;
-                if (key[k] != 0xffffffffu && offset == 0) slot = atomicAdd(cursor + key[k], (unsigned int)length);
-                slot = __shfl_sync(0xffffffffu, slot, head) + offset;
-                if (key[k] != 0xffffffffu) vals[slot] = v[k];
+            if (key != 0xffffffffu && offset == 0) slot = atomicAdd(cursor + key, (unsigned int)length);
+            slot = __shfl_sync(0xffffffffu, slot, head) + offset;
+            if (key != 0xffffffffu) vals[slot] = v;
+            if constexpr (PAIR) {
+                const bool extra = key != 0xffffffffu && key1 != key;
+                if (__any_sync(0xffffffffu, extra) && extra) {   // second copy: mesh-1-only, in mesh 1's brick
+                    VT w = v;
+                    w.x = -fmaxf(l1[0] + 0.5f, 0.f); w.y = fmaxf(l1[1] + 0.5f, 0.f); w.z = fmaxf(l1[2] + 0.5f, 0.f);
+                    vals[atomicAdd(cursor + key1, 1u)] = w;
+                }
             }
         }
     }
@@ -354,11 +389,22 @@ struct Moments {
     }
 };
 
+// sel < 0: plain payload (brick-local coordinates of this mesh).  sel = 0 / 1: PAIR payload, decoded
+// into the coordinates of mesh `sel`; returns false if the copy is not meant for this mesh.
+template <typename VT>
+__device__ __forceinline__ bool unpack_pair(VT &v, int sel) {
+    if (sel < 0) return true;
+    const bool skip = __float_as_int(sel == 0 ? v.x : v.y) < 0;
+    const float off = sel ? -0.5f : -1.f;            // - 1 (stored offset) + 0.5 * sel (mesh shift)
+    v.x = fabsf(v.x) + off; v.y = fabsf(v.y) + off; v.z = fabsf(v.z) + off;
+    return !skip;
+}
+
 template <int S, bool MASS, typename VT>
 __global__ void __launch_bounds__(DEP_THREADS, 2)
 brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
                      DepositGeom G, BrickGrid B, unsigned int *__restrict__ work_counter,
-                     float *__restrict__ mesh) {
+                     float *__restrict__ mesh, int sel) {
     using TD = TileDims<S>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *tile = reinterpret_cast<float *>(smem_raw);
@@ -407,13 +453,14 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
 #pragma unroll
                 for (int k = 0; k < HALF; ++k) {
                     const int i = (h * HALF + k) * DEP_THREADS + tid;
+                    const bool keep = unpack_pair(v[k], sel);
                     int hx, hy, hz;
                     if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
                     else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
                     hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BrickZ<S>::CELLS - 1));
                     const int cell = (hx * BY + hy) * BZ + hz + OFF;          // z-lane = home z + OFF
                     packed[h * HALF + k] = -1;
-                    if (i < nchunk) packed[h * HALF + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
+                    if (i < nchunk && keep) packed[h * HALF + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
                 }
             }
             __syncthreads();
@@ -463,6 +510,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 for (int k = 0; k < HALF; ++k) {
                     const int pk = packed[h * HALF + k];
                     if (pk >= 0) {
+                        unpack_pair(v[k], sel);
                         const int slot = cnt[pk & 8191] + (pk >> 13);
                         sx[slot] = v[k].x; sy[slot] = v[k].y; sz[slot] = v[k].z;
                         if constexpr (MASS) sm[slot] = v[k].m;
@@ -563,24 +611,32 @@ static size_t max_bricks(const apk_plan *P) {
 }
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass) {
+// pair != 0: room for the interlaced twins' shared partition (every particle may need two copies)
+size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int pair) {
     if (np <= 0) return 0;
     const size_t vs = with_mass ? sizeof(P4) : sizeof(P3);
-    return align256(vs * (size_t)np) + 3 * align256(4 * (max_bricks(P) + 2)) + 256;
+    return align256(vs * (size_t)np * (pair ? 2 : 1)) + 3 * align256(4 * (max_bricks(P) + 2)) + 256;
 }
 
-template <int S, typename PT, bool SOA, bool MASS>
+// mesh1 != nullptr: interlaced pair -- G is the shift-0 geometry, mesh1 gets the shift-0.5 twin
+template <int S, typename PT, bool SOA, bool MASS, bool PAIR>
 static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass,
-                      int mass_dtype, long long np, const DepositGeom &G, float *mesh, cudaStream_t st) {
+                      int mass_dtype, long long np, const DepositGeom &G, float *mesh, float *mesh1, cudaStream_t st) {
     using VT = typename std::conditional<MASS, P4, P3>::type;
     const BrickGrid B = make_brick_grid(G, S);
-    const size_t need = deposit_sorted_workspace_bytes(P, np, MASS);
+    DepositGeom G1 = G;
+    if (PAIR) {
+        G1.shift = G.shift + 0.5;
+        if (G.t32 >= 0.f) G1.t32 = G.t32 + 0.5f;
+    }
+    const size_t need = deposit_sorted_workspace_bytes(P, np, MASS, PAIR);
+    APK_REQUIRE(!PAIR || 2 * np < 0xffffffffLL, "apk_deposit_interlaced: more than 2^31 particles on one device");
     APK_REQUIRE(P->workspace && P->workspace_bytes >= need,
                 "apk_deposit: sorted path needs %zu workspace bytes, %zu set (apk_plan_workspace_bytes / apk_plan_set_workspace)",
                 need, P->workspace_bytes);
     APK_REQUIRE(np < 0xffffffffLL, "apk_deposit: more than 2^32-1 particles on one device");
     unsigned char *w = (unsigned char *)P->workspace;
-    VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np);
+    VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np * (PAIR ? 2 : 1));
     const size_t tab = align256(4 * (max_bricks(P) + 2));
     unsigned int *counts = (unsigned int *)w; w += tab;
     unsigned int *brick_start = (unsigned int *)w; w += tab;
@@ -591,19 +647,14 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)P->num_sms * 8);
     P->mark(0, st);
     APK_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)(B.nbricks + 1), st));
-    constexpr bool CANVEC = std::is_same<PT, float>::value;
-    const bool vec = CANVEC && ((((uintptr_t)p0) | (SOA ? ((uintptr_t)p1 | (uintptr_t)p2) : 0)) & 15) == 0;
-    if (vec) brick_count_kernel<S, PT, SOA, CANVEC><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
-    else brick_count_kernel<S, PT, SOA, false><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
+    brick_count_kernel<S, PT, SOA, PAIR><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, G1, B, counts);
     APK_CUDA(cudaGetLastError());
     P->mark(1, st);
     brick_scan_kernel<<<1, 1024, 0, st>>>(counts, B.nbricks, brick_start, cursor);
     APK_CUDA(cudaGetLastError());
     P->mark(2, st);
-    if (vec) brick_scatter_kernel<S, PT, SOA, CANVEC, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
-        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
-    else brick_scatter_kernel<S, PT, SOA, false, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
-        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
+    brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT><<<pb, PART_THREADS, 0, st>>>(
+        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, G1, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
     APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
 
@@ -615,8 +666,13 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     if (per_sm < 1) per_sm = 1;
     const int ctas = std::min(P->num_sms * per_sm, B.nbricks);
     P->mark(3, st);
-    kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, G, B, counter, mesh);
+    kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, G, B, counter, mesh, PAIR ? 0 : -1);
     APK_CUDA(cudaGetLastError());
+    if (PAIR) {
+        APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+        kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, G1, B, counter, mesh1, 1);
+        APK_CUDA(cudaGetLastError());
+    }
     P->mark(4, st);
     P->dep_timed = P->timing;
     P->dep_sorted = true;
@@ -625,31 +681,35 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
 
 template <int S, typename PT, bool SOA>
 static int dispatch_mass(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass,
-                         int mass_dtype, long long np, const DepositGeom &G, float *mesh, cudaStream_t st) {
-    return mass ? run_sorted<S, PT, SOA, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, st)
-                : run_sorted<S, PT, SOA, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, st);
+                         int mass_dtype, long long np, const DepositGeom &G, float *mesh, float *mesh1, cudaStream_t st) {
+    if (mesh1)
+        return mass ? run_sorted<S, PT, SOA, true, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, mesh1, st)
+                    : run_sorted<S, PT, SOA, false, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, mesh1, st);
+    return mass ? run_sorted<S, PT, SOA, true, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, nullptr, st)
+                : run_sorted<S, PT, SOA, false, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, nullptr, st);
 }
 
 template <int S>
 static int dispatch_layout(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
                            const void *mass, int mass_dtype, long long np, const DepositGeom &G, float *mesh,
-                           cudaStream_t st) {
+                           float *mesh1, cudaStream_t st) {
     if (pos_dtype == APK_F32)
-        return layout == APK_SOA ? dispatch_mass<S, float, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, st)
-                                 : dispatch_mass<S, float, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, st);
-    return layout == APK_SOA ? dispatch_mass<S, double, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, st)
-                             : dispatch_mass<S, double, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, st);
+        return layout == APK_SOA ? dispatch_mass<S, float, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, mesh1, st)
+                                 : dispatch_mass<S, float, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, mesh1, st);
+    return layout == APK_SOA ? dispatch_mass<S, double, true>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, mesh1, st)
+                             : dispatch_mass<S, double, false>(P, p0, p1, p2, mass, mass_dtype, np, G, mesh, mesh1, st);
 }
 
 int deposit_atomic_launch(const void *, const void *, const void *, int, int, const void *, int, long long,
                           int, const DepositGeom &, float *, int, cudaStream_t);
 
+// mesh1 != nullptr: also deposit the interlaced twin (shift + 0.5) from the same partition (CIC / TSC only)
 int deposit_sorted_launch(apk_plan *P, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
                           const void *mass, int mass_dtype, long long np, int resampler, const DepositGeom &G,
-                          float *mesh, cudaStream_t st) {
+                          float *mesh, float *mesh1, cudaStream_t st) {
     if (np == 0) return 0;
-    if (resampler == APK_CIC) return dispatch_layout<2>(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, G, mesh, st);
-    if (resampler == APK_TSC) return dispatch_layout<3>(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, G, mesh, st);
+    if (resampler == APK_CIC) return dispatch_layout<2>(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, G, mesh, mesh1, st);
+    if (resampler == APK_TSC) return dispatch_layout<3>(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, G, mesh, mesh1, st);
     // NGP has no halo and no arithmetic worth tiling: one RED per particle
     return deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
 }

@@ -76,6 +76,10 @@ class CudaSlabBackend:
         """Deposit into the slab buffer (with ghost planes); out != None accumulates into it."""
         return self.eng.deposit(pos_aos, mass, resampler, shift, pos_scale, "auto", out=out, zero=out is None)
 
+    def deposit_pair(self, pos_aos, mass, resampler: str, pos_scale: float, out=None):
+        """Both interlaced twins (shift 0, 0.5) from one partition; out = (mesh, mesh_shifted) accumulates."""
+        return self.eng.deposit_pair(pos_aos, mass, resampler, pos_scale, "auto", out=out, zero=out is None)
+
     def accumulate(self, dst: torch.Tensor, src: torch.Tensor) -> None:
         assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
         _lib.call("apk_mesh_accumulate", self.eng._plan, _ptr(dst), _ptr(src), dst.numel(), self.eng.stream)
@@ -250,15 +254,22 @@ class SlabPk:
                 parts.append((fp, fm))
             mark("exchange_particles")
         # 2./3. deposit + ghosts
-        shifts = (0.0, 0.5) if self.interlaced else (0.0,)
         owned = []
-        for sh in shifts:
-            mesh = None
+        if self.interlaced and hasattr(be, "deposit_pair"):
+            pair = None
             for rp, rm in parts:
-                mesh = be.deposit(rp, rm, self.resampler, sh, ps, out=mesh)
+                pair = be.deposit_pair(rp, rm, self.resampler, ps, out=pair)
             mark("deposit")
-            owned.append(self._exchange_ghosts(mesh))
+            owned = [self._exchange_ghosts(m) for m in pair]
             mark("ghosts")
+        else:
+            for sh in ((0.0, 0.5) if self.interlaced else (0.0,)):
+                mesh = None
+                for rp, rm in parts:
+                    mesh = be.deposit(rp, rm, self.resampler, sh, ps, out=mesh)
+                mark("deposit")
+                owned.append(self._exchange_ghosts(mesh))
+                mark("ghosts")
         total = be.mesh_sum(owned[0])
         # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
         grids = [be.fft2d(o) for o in owned]

@@ -105,9 +105,10 @@ class PkEngine:
         planes = self.n0 + (self.ghost_lo + self.ghost_hi if ghosts else 0)
         return torch.empty((planes, self.N, self.ldz), dtype=torch.float32, device=self.device)
 
-    def ensure_workspace(self, max_particles: int, with_mass: bool) -> None:
+    def ensure_workspace(self, max_particles: int, with_mass: bool, interlaced: bool = False) -> None:
         need = ct.c_size_t()
-        _lib.call("apk_plan_workspace_bytes", self._plan, int(max_particles), int(with_mass), ct.byref(need))
+        _lib.call("apk_plan_workspace_bytes", self._plan, int(max_particles), int(with_mass), int(interlaced),
+                  ct.byref(need))
         if self._workspace is None or self._workspace.numel() < need.value:
             self._workspace = None
             self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
@@ -183,6 +184,38 @@ class PkEngine:
         del keep
         return out
 
+    def deposit_pair(self, pos, mass=None, resampler: str = "tsc", pos_scale: float | None = None,
+                     method: str = "auto", out: tuple | None = None, zero: bool = True) -> tuple:
+        """The interlaced twins (shift 0 and 0.5) in one call: one brick partition serves both meshes."""
+        rs = _lib.RESAMPLERS.get(str(resampler).lower())
+        if rs is None:
+            raise AstrildPkError(f"unknown resampler {resampler!r}")
+        p0, p1, p2, layout, dt, npart, keep = self._positions(pos)
+        m = None
+        if mass is not None and not np.isscalar(mass):
+            m = self._to_device(mass).contiguous()
+            if m.ndim != 1 or m.shape[0] != npart:
+                raise AstrildPkError("mass must be a scalar or have one entry per particle")
+        slab = self.n0 < self.N
+        m0, m1 = out if out is not None else (self.new_mesh(ghosts=slab), self.new_mesh(ghosts=slab))
+        self.ensure_workspace(npart, m is not None, True)
+        _lib.call("apk_deposit_interlaced", self._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout,
+                  _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64,
+                  float(1.0 / self.L if pos_scale is None else pos_scale), _ptr(m),
+                  _lib.APK_F32 if (m is None or m.dtype == torch.float32) else _lib.APK_F64,
+                  int(npart), rs, _lib.DEPOSIT_METHODS[method], int(bool(zero)), _ptr(m0), _ptr(m1), self.stream)
+        if mass is not None and np.isscalar(mass) and float(mass) != 1.0:
+            m0.mul_(float(mass)); m1.mul_(float(mass))
+        del keep
+        return m0, m1
+
+    def _deposit_shifts(self, pos, mass, resampler, shifts, pos_scale, method, meshes, zero):
+        if tuple(shifts) == (0.0, 0.5):
+            self.deposit_pair(pos, mass, resampler, pos_scale, method, out=(meshes[0], meshes[1]), zero=zero)
+        else:
+            for mesh, sh in zip(meshes, shifts):
+                self.deposit(pos, mass, resampler, sh, pos_scale, method, out=mesh, zero=zero)
+
     def deposit_many(self, pos, mass=None, resampler: str = "tsc", shifts=(0.0,), pos_scale: float | None = None,
                      method: str = "auto", chunk_rows: int = 1 << 25) -> list:
         """One mesh per entry of ``shifts`` (interlacing: (0, 0.5)) from the same particles.
@@ -201,8 +234,8 @@ class PkEngine:
             dev = self._positions(pos)           # one upload shared by all shifts
             dpos = (dev[0], dev[1], dev[2]) if dev[3] == _lib.APK_SOA else dev[0]
             dmass = None if (mass is None or np.isscalar(mass)) else self._to_device(mass)
-            for mesh, sh in zip(meshes, shifts):
-                self.deposit(dpos, dmass if dmass is not None else mass, resampler, sh, pos_scale, method, out=mesh)
+            self._deposit_shifts(dpos, dmass if dmass is not None else mass, resampler, shifts, pos_scale, method,
+                                 meshes, True)
             return meshes
 
         def as_host_tensor(a):
@@ -218,7 +251,7 @@ class PkEngine:
                 for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [None, None]
-        self.ensure_workspace(chunk_rows, hmass is not None)
+        self.ensure_workspace(chunk_rows, hmass is not None, len(shifts) == 2)
         for c, a in enumerate(range(0, npart, chunk_rows)):
             b = min(a + chunk_rows, npart)
             s = c & 1
@@ -232,8 +265,7 @@ class PkEngine:
             part = [buf[: b - a] for buf in bufs[s]]
             ppos = tuple(part[:3]) if cols is not None else part[0]
             pm = part[-1] if hmass is not None else mass
-            for mesh, sh in zip(meshes, shifts):
-                self.deposit(ppos, pm, resampler, sh, pos_scale, method, out=mesh, zero=(c == 0))
+            self._deposit_shifts(ppos, pm, resampler, shifts, pos_scale, method, meshes, c == 0)
             free[s] = torch.cuda.Event()
             free[s].record(cur)
         cur.wait_stream(copy_stream)

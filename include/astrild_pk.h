@@ -55,8 +55,10 @@ int apk_plan_create(apk_plan **plan, int nmesh, double boxsize, int x0, int n0, 
 int apk_plan_destroy(apk_plan *plan);
 /* floats in one local mesh: n0 * N * 2*(N/2+1)                                               */
 int apk_plan_mesh_elems(const apk_plan *plan, int64_t *elems);
-/* bytes of scratch apk_deposit (sorted path, max_particles) and apk_fft_r2c need            */
-int apk_plan_workspace_bytes(const apk_plan *plan, int64_t max_particles, int with_mass, size_t *bytes);
+/* bytes of scratch apk_deposit (sorted path, max_particles; interlaced != 0: apk_deposit_interlaced)
+ * and apk_fft_r2c need                                                                         */
+int apk_plan_workspace_bytes(const apk_plan *plan, int64_t max_particles, int with_mass, int interlaced,
+                             size_t *bytes);
 int apk_plan_set_workspace(apk_plan *plan, void *workspace, size_t bytes);
 /* slab plans deposit into n_lo + n0 + n_hi planes (ghosts below/above the owned slab, to be
  * sent to and added by the ring neighbours); single-GPU plans report 0, 0.                    */
@@ -84,6 +86,15 @@ int apk_binning_last_ms(apk_binning *binning, float ms[2]);
 int apk_deposit(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
                 int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
                 int resampler, double shift, int method, int zero_first, float *mesh, void *stream);
+
+/* Both meshes of nbodykit's interlacing (CatalogMesh interlaced=True: a second paint with the
+ * particles shifted by half a cell, src/astrild/power_spectra/power_spectrum_3d.py:201,209 ask for
+ * it) in one call: `mesh` gets shift 0, `mesh_shifted` shift 0.5.  The sorted path builds ONE brick
+ * partition for both (boundary particles are filed twice).  Same arguments as apk_deposit.       */
+int apk_deposit_interlaced(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
+                           int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
+                           int resampler, int method, int zero_first, float *mesh, float *mesh_shifted,
+                           void *stream);
 
 /* ---- slab routing (multi-GPU) ---------------------------------------------------------------- */
 /* Extracts the particles that must LEAVE this rank: destination = owner of the x-slab holding

@@ -298,3 +298,19 @@ def test_streamed_host_deposit_matches_device_deposit(ab, oracle_fast):
     r2 = ab.FFTPower(ab.CatalogMesh(torch.from_numpy(pos).cuda(), L, N, resampler="cic", normalize=True), mode="1d",
                      kmin=2 * np.pi / L)
     np.testing.assert_allclose(r1.power["power"].real, r2.power["power"].real, rtol=1e-6)
+
+
+@pytest.mark.parametrize("resampler", ["cic", "tsc"])
+@pytest.mark.parametrize("method", ["sorted", "atomic"])
+def test_interlaced_pair_deposit_matches_two_deposits(ab, oracle_fast, resampler, method):
+    """apk_deposit_interlaced (one shared partition) == two independent deposits == oracle."""
+    N, L = 50, 777.0
+    pos, mass = _particles(21, 400000, L, -0.1, 1.1)
+    eng = ab.get_engine(N, L)
+    for m in (None, mass):
+        pair = eng.deposit_pair(pos, m, resampler, method=method)
+        for mesh, sh in zip(pair, (0.0, 0.5)):
+            want = oracle_fast.paint(pos, m, N, L, resampler, sh)
+            got = eng.store_mesh(mesh).cpu().numpy()
+            np.testing.assert_allclose(got, want, rtol=0, atol=3e-6 * want.max())
+            assert got.sum() == pytest.approx(want.sum(), rel=1e-6)

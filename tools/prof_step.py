@@ -21,11 +21,12 @@ comp = (wl["resampler"], wl["interlaced"]) if wl["compensated"] else None
 binning = eng.binning(kmin=2 * np.pi / L, compensation=comp, interlaced=wl["interlaced"])
 mesh1 = eng.new_mesh()
 mesh2 = eng.new_mesh() if wl["interlaced"] else None
-eng.ensure_workspace(n ** 3, False)
+eng.ensure_workspace(n ** 3, False, wl["interlaced"])
 for _ in range(steps):
-    eng.deposit(pos, None, wl["resampler"], 0.0, 1.0, "sorted", out=mesh1)
     if mesh2 is not None:
-        eng.deposit(pos, None, wl["resampler"], 0.5, 1.0, "sorted", out=mesh2)
+        eng.deposit_pair(pos, None, wl["resampler"], 1.0, "sorted", out=(mesh1, mesh2))
+    else:
+        eng.deposit(pos, None, wl["resampler"], 0.0, 1.0, "sorted", out=mesh1)
     c1 = eng.r2c(mesh1)
     c1s = eng.r2c(mesh2) if mesh2 is not None else None
     res = eng.bin_power(binning, c1, c1s, scale=1.0)
