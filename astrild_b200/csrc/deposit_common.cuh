@@ -40,6 +40,15 @@ __host__ __device__ __forceinline__ int wrap_index32(int i, int N) {
     return i;
 }
 
+// branch-free wrap for indices within one box length of the box; `far` collects the others so the
+// caller can take ONE rare slow path per particle instead of a division per axis
+__device__ __forceinline__ int wrap_near(int i, int N, bool &far) {
+    i += (i < 0) ? N : 0;
+    i -= (i >= N) ? N : 0;
+    far |= (unsigned)i >= (unsigned)N;
+    return i;
+}
+
 __host__ __device__ __forceinline__ int DepositGeom::local_plane(long long ix) const {
     const int gx = wrap_index(ix, N);
     if (!slab) return gx;

@@ -113,7 +113,7 @@ __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const Dep
 // products within ~1e-13 of an integer, where the window weights are continuous anyway.
 template <int S>
 __device__ __forceinline__ unsigned int brick_of_f32(const float *x, const DepositGeom &G, const BrickGrid &B,
-                                                     float (&l)[3]) {
+                                                     float (&l)[3], bool &far) {
     int b[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -125,7 +125,7 @@ __device__ __forceinline__ unsigned int brick_of_f32(const float *x, const Depos
         float f = __fadd_rn(__fsub_rn(p, h), e);     // p - h is exact; f in [e, 1 + e)
         if (d == 0 && G.slab) {                      // ownership: floor of the UNSHIFTED coordinate
             const int hu = (int)(h + floorf(f));
-            int rel = wrap_index32(hu, G.N) - G.own0;
+            const int rel = wrap_near(hu, G.N, far) - G.own0;
             if (rel < 0 || rel >= G.nown) return 0xffffffffu;
         }
         f += G.t32;                                  // + shift (+ 0.5: TSC rounds to the nearest cell)
@@ -133,11 +133,12 @@ __device__ __forceinline__ unsigned int brick_of_f32(const float *x, const Depos
         h += c;
         f -= c;                                      // [0, 1)
         const float frac = (S == 2) ? f : f - 0.5f;  // relative to the home cell
-        int hl = wrap_index32((int)h, G.N);
+        int hl = wrap_near((int)h, G.N, far);
         if (d == 0 && G.slab) {
             hl -= G.plane0;
-            if (hl < 0) hl += G.N; else if (hl >= G.N) hl -= G.N;
-            if (hl >= G.nplanes) hl = 0;
+            hl += (hl < 0) ? G.N : 0;
+            hl -= (hl >= G.N) ? G.N : 0;
+            hl = (hl >= G.nplanes) ? 0 : hl;
         }
         const int edge = d == 0 ? BX : (d == 1 ? BY : BrickZ<S>::CELLS);
         b[d] = hl / edge;
@@ -150,7 +151,11 @@ template <int S, typename PT>
 __device__ __forceinline__ unsigned int brick_of_any(const PT *x, const DepositGeom &G, const BrickGrid &B,
                                                      float (&l)[3]) {
     if constexpr (std::is_same<PT, float>::value) {
-        if (G.t32 >= 0.f) return brick_of_f32<S>(x, G, B, l);
+        if (G.t32 >= 0.f) {
+            bool far = false;                        // position more than a box length outside the box (rare)
+            const unsigned int key = brick_of_f32<S>(x, G, B, l, far);
+            if (!far) return key;
+        }
     }
     const double xd[3] = {(double)x[0], (double)x[1], (double)x[2]};
     return brick_of<S>(xd, G, B, l);

@@ -42,6 +42,7 @@ class CudaSlabBackend:
         self.device = self.eng.device
         self.N, self.L, self.n0, self.nranks = N, L, n0, nranks
         self._counts = torch.zeros(2 * nranks, dtype=torch.int64, device=self.device)
+        self.side_stream = torch.cuda.Stream(self.device)     # transposes overlap the FFTs of the other field
 
     # -- 1. routing -----------------------------------------------------------------------
     def route(self, pos, mass, pos_scale: float):
@@ -272,13 +273,39 @@ class SlabPk:
                 mark("ghosts")
         total = be.mesh_sum(owned[0])
         # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
-        grids = [be.fft2d(o) for o in owned]
-        mark("fft2d")
-        grids = self._transpose(grids)
-        del owned
-        mark("transpose")
-        grids = [be.fft1d(g, self.ny) for g in grids]
-        mark("fft1d")
+        #    pipelined per field: while field f is packed and exchanged on a side stream, the 2-D FFT of
+        #    field f+1 (and later the 1-D FFT of field f-1) runs on the main stream
+        side = getattr(be, "side_stream", None)
+        if side is None or P == 1 or len(owned) == 1:
+            grids = [be.fft2d(o) for o in owned]
+            mark("fft2d")
+            grids = self._transpose(grids)
+            del owned
+            mark("transpose")
+            grids = [be.fft1d(g, self.ny) for g in grids]
+            mark("fft1d")
+        else:
+            main = torch.cuda.current_stream(be.device)
+            moved, done = [], []
+            for o in owned:
+                g2 = be.fft2d(o)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                o.record_stream(side)
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    t = self._transpose([g2])[0]
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                t.record_stream(main)
+                moved.append(t)
+                done.append(ev)
+            grids = []
+            for t, ev in zip(moved, done):
+                main.wait_event(ev)
+                grids.append(be.fft1d(t, self.ny))
+            del owned
+            mark("fft+transpose")
         # 7. binning on the transposed slab
         comp = (self.resampler, self.interlaced) if self.compensated else None
         binning = be.make_binning(self.y0, self.ny, kmin, dk, kmax, comp, self.interlaced)

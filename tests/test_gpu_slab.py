@@ -75,6 +75,7 @@ def _run_emulated(P, N, L, pos, mass, kw):
             torch.cuda.set_device(0)
             runner = distributed.SlabPk(N, L, device="cuda:0", comm=ThreadComm(shared, rank),
                                         resampler=kw["resampler"], interlaced=kw["interlaced"], compensated=kw["compensated"])
+            runner.backend.side_stream = None      # the in-memory comm has no cross-thread stream ordering
             results[rank] = runner.power(pos[rank::P], None if mass is None else mass[rank::P], kmin=2 * np.pi / L,
                                          normalize=kw["normalize"])
         except BaseException as e:  # noqa: BLE001
