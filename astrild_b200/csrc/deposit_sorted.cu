@@ -8,26 +8,29 @@
 // traffic is real but not credited.
 //
 // Pipeline (all on one stream, no host sync):
-//   1. brick_count_kernel   every particle -> key of the 12x12x32-cell brick that holds its HOME
-//                           cell (float64 index arithmetic, identical to the oracle's); per-brick
-//                           counts with warp-aggregated RED (__match_any_sync: one atomic per run
-//                           of equal keys in a warp -- snapshot order is spatially coherent).
+//   1. brick_count_kernel   every particle -> key of the brick (12 x 12 x 30 home cells for TSC, 12 x 12 x 31
+//                           for CIC) that holds its HOME cell; per-brick counts with one RED per warp-run of
+//                           equal keys (snapshot order is spatially coherent).  float32 positions use an
+//                           error-free float32 product (no FP64 issue slots), float64 positions the oracle's
+//                           float64 expression; both put every particle in the oracle's cell.
 //   2. brick_scan_kernel    exclusive scan of the counts -> brick_start[], cursors.
-//   3. brick_scatter_kernel keys are recomputed (never stored); each run of equal keys claims
-//                           its slots with ONE atomicAdd on the brick's cursor and writes its
-//                           payload = brick-local coordinates as 3 floats (+ mass), contiguously.
-//                           One read and one write of the particles replace a multi-pass radix
-//                           sort; order inside a brick is arbitrary (the deposit does not care).
-//   4. brick_deposit_kernel persistent CTAs pull bricks from a counter; per brick and per chunk
-//      of <= CH particles: counting-sort the chunk by home cell inside shared memory (native
-//      32-bit ATOMS.ADD gives each particle its rank), then one thread per home cell sums the
-//      S^3 window moments of its own particles in registers.  The moments are spread WITHOUT
-//      atomics (shared-memory float atomics are CAS loops on sm_100): lanes of a warp are the 32
-//      z-cells of one (x,y) column, so the z-spread is two warp shuffles, and the (x,y)-spread is
-//      a plain load/add/store into the shared tile that is conflict-free because the 16 columns
-//      active at a time are 3 cells apart in x and y (9 colour classes, one __syncthreads each).
-//      The finished (12+S-1)^2 x (32+S-1) tile is added to the mesh with RED.ADD.F32, skipping
-//      zeros; bricks are visited x-major so neighbouring tiles meet in L2.
+//   3. brick_scatter_kernel keys are recomputed (never stored); each run of equal keys claims its slots with ONE
+//                           atomicAdd on the brick's cursor and writes its payload = brick-local coordinates as
+//                           3 floats (+ mass), contiguously.  One read and one write of the particles replace a
+//                           multi-pass radix sort; order inside a brick is arbitrary (the deposit does not care).
+//      PAIR mode (apk_deposit_interlaced): one partition serves both interlaced meshes -- particles whose
+//      two home cells fall in different bricks (~11 %) are filed twice, sign bits of the payload say which
+//      mesh a copy is for.
+//   4. brick_deposit_kernel persistent CTAs pull bricks from a counter; per brick and per chunk of <= CH
+//      particles: counting-sort the chunk by home cell inside shared memory (native 32-bit ATOMS.ADD gives each
+//      particle its rank), then one thread per home cell sums the S^3 window moments of its own particles in
+//      registers (packed FFMA2).  The moments are spread WITHOUT atomics (shared-memory float atomics are CAS
+//      loops on sm_100): the 32 lanes of a warp are the 32 tile cells of one (x,y) column along z (30 home
+//      cells + 2 halo lanes for TSC), so the z-spread is two warp shuffles with no edge cases, and the
+//      (x,y)-spread is a plain load/add/store into the shared tile that is conflict-free because the 16
+//      columns active at a time are 3 cells apart in x and y (9 colour classes, one __syncthreads each).
+//      The finished 14 x 14 x 32 (TSC) tile is added to the mesh with RED.ADD.V2.F32 on aligned pairs,
+//      skipping zeros; bricks are visited x-major so neighbouring tiles meet in L2.
 #include "apk_common.cuh"
 #include "deposit_common.cuh"
 #include <algorithm>
@@ -111,29 +114,43 @@ __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const Dep
 // p = fl(x*s0) and e = the exact rounding error of p plus x*(s1 + s2): an error-free product good
 // to ~2^-70, so floor() and the in-cell fraction agree with the float64 expression except for
 // products within ~1e-13 of an integer, where the window weights are continuous anyway.
-template <int S>
-__device__ __forceinline__ unsigned int brick_of_f32(const float *x, const DepositGeom &G, const BrickGrid &B,
-                                                     float (&l)[3], bool &far) {
-    int b[3];
+// float32 index path in two steps so that the interlaced twins share the first one:
+//   f32_base   : floor and fraction of the UNSHIFTED coordinate per axis (+ slab ownership)
+//   f32_finish : home cell / brick / brick-local coordinate for one mesh (shift folded into t32)
+struct AxisBase { float h[3], f[3]; bool owned; };
+
+__device__ __forceinline__ AxisBase f32_base(const float *x, const DepositGeom &G, bool &far) {
+    AxisBase a;
+    a.owned = true;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         const float p = __fmul_rn(x[d], G.s0);      // intrinsics: never contracted into an FMA
         float e = fmaf(x[d], G.s0, -p);
         e = fmaf(x[d], G.s1, e);
         e = fmaf(x[d], G.s2, e);
-        float h = floorf(p);
-        float f = __fadd_rn(__fsub_rn(p, h), e);     // p - h is exact; f in [e, 1 + e)
+        a.h[d] = floorf(p);
+        a.f[d] = __fadd_rn(__fsub_rn(p, a.h[d]), e);   // p - h is exact; f in [e, 1 + e)
         if (d == 0 && G.slab) {                      // ownership: floor of the UNSHIFTED coordinate
-            const int hu = (int)(h + floorf(f));
+            const int hu = (int)(a.h[0] + floorf(a.f[0]));
             const int rel = wrap_near(hu, G.N, far) - G.own0;
-            if (rel < 0 || rel >= G.nown) return 0xffffffffu;
+            a.owned = rel >= 0 && rel < G.nown;
         }
-        f += G.t32;                                  // + shift (+ 0.5: TSC rounds to the nearest cell)
+    }
+    return a;
+}
+
+template <int S>
+__device__ __forceinline__ unsigned int f32_finish(const AxisBase &a, float t32, const DepositGeom &G,
+                                                   const BrickGrid &B, float (&l)[3], bool &far) {
+    if (!a.owned) return 0xffffffffu;
+    int b[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float f = a.f[d] + t32;                      // + shift (+ 0.5: TSC rounds to the nearest cell)
         const float c = floorf(f);
-        h += c;
         f -= c;                                      // [0, 1)
         const float frac = (S == 2) ? f : f - 0.5f;  // relative to the home cell
-        int hl = wrap_near((int)h, G.N, far);
+        int hl = wrap_near((int)(a.h[d] + c), G.N, far);
         if (d == 0 && G.slab) {
             hl -= G.plane0;
             hl += (hl < 0) ? G.N : 0;
@@ -147,18 +164,24 @@ __device__ __forceinline__ unsigned int brick_of_f32(const float *x, const Depos
     return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
 }
 
-template <int S, typename PT>
-__device__ __forceinline__ unsigned int brick_of_any(const PT *x, const DepositGeom &G, const BrickGrid &B,
-                                                     float (&l)[3]) {
+// keys and brick-local coordinates of one particle for mesh 0 (G) and, if PAIR, its interlaced twin (G1)
+template <int S, typename PT, bool PAIR>
+__device__ __forceinline__ void brick_keys(const PT *x, const DepositGeom &G, const DepositGeom &G1, const BrickGrid &B,
+                                           unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3]) {
     if constexpr (std::is_same<PT, float>::value) {
-        if (G.t32 >= 0.f) {
+        if (G.t32 >= 0.f && (!PAIR || G1.t32 >= 0.f)) {
             bool far = false;                        // position more than a box length outside the box (rare)
-            const unsigned int key = brick_of_f32<S>(x, G, B, l, far);
-            if (!far) return key;
+            const AxisBase a = f32_base(x, G, far);
+            key0 = f32_finish<S>(a, G.t32, G, B, l0, far);
+            key1 = key0;
+            if (PAIR) key1 = f32_finish<S>(a, G1.t32, G1, B, l1, far);
+            if (!far) return;
         }
     }
     const double xd[3] = {(double)x[0], (double)x[1], (double)x[2]};
-    return brick_of<S>(xd, G, B, l);
+    key0 = brick_of<S>(xd, G, B, l0);
+    key1 = key0;
+    if (PAIR) key1 = brick_of<S>(xd, G1, B, l1);
 }
 
 // raw coordinates of this thread's 4 particles of a tile, v[3*k + d]: slice k of the tile is the
@@ -215,15 +238,14 @@ brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const P
         if (base + step < np) load4<PT, SOA>(p0, p1, p2, first + step, PART_THREADS, np, nxt);   // next tile in flight
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float l[3];
-            unsigned int key = brick_of_any<S, PT>(cur.v + 3 * k, G, B, l);
+            float l[3], l1[3];
+            unsigned int key, key1;
+            brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1);
             if (first + (long long)k * PART_THREADS >= np) key = 0xffffffffu;
             int head, offset, length;
             warp_runs(key, lane, head, offset, length);
             if (key != 0xffffffffu && offset == 0) atomicAdd(counts + key, (unsigned int)length);
             if constexpr (PAIR) {
-                float l1[3];
-                const unsigned int key1 = brick_of_any<S, PT>(cur.v + 3 * k, G1, B, l1);
                 const bool extra = key != 0xffffffffu && key1 != key;
                 if (__any_sync(0xffffffffu, extra) && extra) atomicAdd(counts + key1, 1u);
             }
@@ -285,8 +307,9 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const long long p = first + (long long)k * PART_THREADS;
-            float l[3];
-            unsigned int key = brick_of_any<S, PT>(cur.v + 3 * k, G, B, l);
+            float l[3], l1[3];
+            unsigned int key, key1;
+            brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1);
             if (p >= np) key = 0xffffffffu;
             VT v;
             v.x = l[0]; v.y = l[1]; v.z = l[2];
@@ -294,10 +317,7 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
                 const long long pc = min(p, np - 1);
                 v.m = mass_f64 ? (float)((const double *)mass)[pc] : ((const float *)mass)[pc];
             }
-            unsigned int key1 = key;
-            float l1[3];
             if constexpr (PAIR) {
-                key1 = brick_of_any<S, PT>(cur.v + 3 * k, G1, B, l1);
                 v.x = fmaxf(l[0] + 1.f, 0.f); v.y = fmaxf(l[1] + 1.f, 0.f); v.z = fmaxf(l[2] + 1.f, 0.f);
                 if (key1 != key) v.y = -v.y;                     // first copy is mesh-0-only
             }
