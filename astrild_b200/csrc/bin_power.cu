@@ -133,12 +133,19 @@ bin_power_kernel(BinArgs A) {
         double n_kb2 = 0.0;                      // b-row tables travel with the prefetched row
         float n_icb = 1.f;
         float2 n_phb = make_float2(1.f, 0.f);
+        // smallest kz^2 of this warp's 32 modes (kz^2 grows with iz): if even that one is beyond the last
+        // edge, the whole 256-byte line is overflow and is not read at all (for kmax = Nyquist ~40 % of
+        // the grid lies outside the sphere)
+        const double kz2_min = __shfl_sync(0xffffffffu, kz2, 0);
+        double pre_kb2 = A.kb2[min(ib0, A.n_b - 1)];     // kb2 runs one more row ahead: the skip test must not wait for it
         auto load_row = [&](int ib) {
-            n_kb2 = A.kb2[ib];
+            n_kb2 = pre_kb2;
+            pre_kb2 = A.kb2[min(ib + 1, A.n_b - 1)];
             if (COMP) n_icb = A.ic_b[ib];
             if (INTERLACED) n_phb = A.ph_b[ib];
 #pragma unroll
             for (int t = 0; t < BIN_TA; ++t) {
+                if ((ka2[t] + n_kb2) + kz2_min >= e2_last) continue;      // warp-uniform
                 const size_t idx = base[t] + (size_t)ib * A.nz;
                 v1[t] = __ldcs(A.c1 + idx);
                 if (INTERLACED) v1s[t] = __ldcs(A.c1s + idx);
