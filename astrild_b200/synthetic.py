@@ -63,3 +63,31 @@ def zeldovich_particles(n_side: int, boxsize: float, seed: int, device, rms_cell
         cols.append(pos.contiguous())
         del psi
     return tuple(cols)
+
+
+def sine_displaced_particles(n_side: int, seed: int, device, rms_cells: float = 1.0, x_planes: tuple | None = None) -> tuple:
+    """Config 5 (2048^3, per-rank generation): lattice q = (i + 1/2)/n displaced by a smooth analytic field
+    (a few plane waves per axis, phases from ``seed``) with rms 1-D displacement ``rms_cells`` lattice
+    spacings.  No global FFT is needed, so each rank builds only its own planes.  Returns (x, y, z) float32
+    in [0, 1)."""
+    n = n_side
+    a, b = (0, n) if x_planes is None else x_planes
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    nwave = 6
+    kv = torch.randint(1, 9, (3, nwave, 3), generator=g).to(device=device, dtype=torch.float32)   # wave vectors
+    ph = (torch.rand((3, nwave), generator=g) * 2 * math.pi).to(device)
+    amp = rms_cells / n * math.sqrt(2.0 / nwave)
+    lat = (torch.arange(n, device=device, dtype=torch.float32) + 0.5) / n
+    qx, qy, qz = lat[a:b, None, None], lat[None, :, None], lat[None, None, :]
+    cols = []
+    for axis in range(3):
+        disp = torch.zeros((b - a, n, n), device=device, dtype=torch.float32)
+        for w in range(nwave):
+            disp += torch.sin(2 * math.pi * (kv[axis, w, 0] * qx + kv[axis, w, 1] * qy + kv[axis, w, 2] * qz) + ph[axis, w])
+        q = (qx, qy, qz)[axis]
+        pos = (q + amp * disp).reshape(-1)
+        del disp
+        pos = pos - torch.floor(pos)
+        pos = torch.where(pos >= 1.0, torch.zeros_like(pos), pos)
+        cols.append(pos.contiguous())
+    return tuple(cols)

@@ -37,6 +37,8 @@ WORKLOADS = {
     "c3": dict(n=1024, mesh=1024, box=1000.0, resampler="tsc", interlaced=True, compensated=True, seed=31337,
                kind="zeldovich", name="c3: 1024^3 Zel'dovich particles, TSC + interlacing + compensation, 1024^3 mesh"),
 }
+WORKLOADS["c5"] = dict(n=2048, mesh=2048, box=1000.0, resampler="cic", interlaced=False, compensated=False, seed=4242,
+                       kind="sine", name="c5: 2048^3 particles (lattice + smooth analytic displacement), CIC, 2048^3 mesh, 8 GPUs")
 # diagnostics only (not BASELINE configs): a half-size c3 for profiling, and an incoherent-order c2
 WORKLOADS["c3s"] = dict(WORKLOADS["c3"], n=512, mesh=512, name="c3s: 512^3 particles, TSC + interlacing + compensation, 512^3 mesh (profiling)")
 WORKLOADS["c2u"] = dict(WORKLOADS["c2"], kind="uniform", name="c2u: 512^3 uniform-random particles (incoherent order), CIC, 512^3 mesh")
@@ -238,8 +240,12 @@ def run_ours(args, wl_key: str) -> None:
         runner = distributed.SlabPk(N, L, resampler=wl["resampler"], interlaced=wl["interlaced"],
                                     compensated=wl["compensated"], device=dev)
         a, b = runner.lattice_planes(n)
-        pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev, x_planes=(a, b)) if wl["kind"] == "zeldovich" \
-            else tuple(c[rank::world].contiguous() for c in synthetic.uniform_particles(n, wl["seed"], dev))
+        if wl["kind"] == "zeldovich":
+            pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev, x_planes=(a, b))
+        elif wl["kind"] == "sine":
+            pos = synthetic.sine_displaced_particles(n, wl["seed"], dev, x_planes=(a, b))
+        else:
+            pos = tuple(c[rank::world].contiguous() for c in synthetic.uniform_particles(n, wl["seed"], dev))
         torch.cuda.empty_cache()
 
         def step():
@@ -253,6 +259,8 @@ def run_ours(args, wl_key: str) -> None:
     else:
         if wl["kind"] == "zeldovich":
             pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev)
+        elif wl["kind"] == "sine":
+            pos = synthetic.sine_displaced_particles(n, wl["seed"], dev)
         else:
             pos = synthetic.uniform_particles(n, wl["seed"], dev)
         torch.cuda.empty_cache()
@@ -328,10 +336,12 @@ def run_ours(args, wl_key: str) -> None:
     value = Np / (ms_per_step * 1e-3) / 1e6
 
     # ---------------- end to end through the public API, host buffers ------------------------
-    host_pos = [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in pos]
+    if args.no_e2e:
+        h2d = 0
+    host_pos = [] if args.no_e2e else [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in pos]
     for h, c in zip(host_pos, pos):
         h.copy_(c)
-    h2d = sum(h.numel() * h.element_size() for h in host_pos)
+    h2d = sum(h.numel() * h.element_size() for h in host_pos) if host_pos else 0
     cpu_sp, cpu_planes = 1 << 23, 64
     cpu_pos = None
     if world == 1 and not args.no_cpu_baseline:      # the CPU baseline times a prefix of the SAME particles
@@ -340,20 +350,22 @@ def run_ours(args, wl_key: str) -> None:
         del pos
         torch.cuda.empty_cache()
     e2e_steps = max(1, min(args.steps, 5))
-    e2e_step(host_pos)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pw = e2e_step(host_pos)
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        e2e_step(host_pos)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pw = e2e_step(host_pos)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     nb1 = len(res["edges"]) + 1
     d2h = 4 * nb1 * 8 + 16
-    e2e = {"value": Np / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world) if world > 1 else int(h2d),
+    e2e = None if args.no_e2e else {"value": Np / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world) if world > 1 else int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
            "api": "astrild_b200.CatalogMesh(host x,y,z pinned) -> FFTPower(mode='1d', kmin=2pi/L)"}
 
@@ -436,7 +448,7 @@ def pick_workload(args) -> str:
         if torch.cuda.is_available():
             free, total = torch.cuda.mem_get_info(int(os.environ.get("LOCAL_RANK", "0")))
             world = int(os.environ.get("WORLD_SIZE", "1"))
-            return "c3" if free * world > 110e9 else "c2"
+            return "c3" if free > 60e9 / world + 20e9 else "c2"
     except Exception:
         pass
     return "c3"
@@ -450,6 +462,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (diagnostic runs only)")
     args = ap.parse_args()
     wl = pick_workload(args)
     if args.impl == "reference":
