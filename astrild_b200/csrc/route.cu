@@ -25,29 +25,60 @@ __device__ __forceinline__ void warp_runs_r(int key, int lane, int &head, int &o
     length = (above ? __ffs(above) - 1 : 32) - head;
 }
 
-template <typename PT, bool SOA>
-__device__ __forceinline__ int dest_rank(const PT *__restrict__ p0, long long p, double scale, int N, int planes_per_rank) {
-    const double g = (double)(SOA ? p0[p] : p0[3 * p]) * scale;
-    long long i = (long long)floor(g);
-    return wrap_index(i, N) / planes_per_rank;
+struct RouteGeom {
+    double scale;        // grid units per position unit
+    float s0, s1, s2;    // scale as three floats (error-free float32 product, see deposit_sorted.cu)
+    int N, ppr, self, x0;
+};
+
+// destination rank of a particle, or -1 if it stays (the common case costs no integer division)
+template <typename PT>
+__device__ __forceinline__ int dest_rank(const PT x, const RouteGeom &R) {
+    int cell;
+    bool far = false;
+    if constexpr (sizeof(PT) == 4) {
+        const float pr = __fmul_rn(x, R.s0);
+        float e = fmaf(x, R.s0, -pr);
+        e = fmaf(x, R.s1, e);
+        e = fmaf(x, R.s2, e);
+        const float h = floorf(pr);
+        const float f = __fadd_rn(__fsub_rn(pr, h), e);
+        cell = wrap_near((int)(h + floorf(f)), R.N, far);
+        far |= !(fabsf(pr) < 1.0e9f);
+    } else {
+        far = true;
+    }
+    if (far) cell = wrap_index((long long)floor((double)x * R.scale), R.N);
+    const int rel = cell - R.x0;
+    if (rel >= 0 && rel < R.ppr) return -1;
+    return cell / R.ppr;
 }
 
 // pass 1: how many of my particles belong to each OTHER rank (the ones that stay are not touched:
 // the slab deposit skips particles it does not own, so only leavers are copied and sent)
 template <typename PT, bool SOA>
 __global__ void __launch_bounds__(256)
-route_count_kernel(const PT *__restrict__ p0, long long np, double scale, int N, int ppr, int self,
-                   unsigned long long *__restrict__ counts) {
+route_count_kernel(const PT *__restrict__ p0, long long np, RouteGeom R, unsigned long long *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long np_pad = (np + 31) & ~31LL;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += stride) {
-        int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
-        if (d == self) d = -1;
-        if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;        // the usual case: nobody leaves
-        int head, offset, length;
-        warp_runs_r(d, lane, head, offset, length);
-        if (d >= 0 && offset == 0) atomicAdd(counts + d, (unsigned long long)length);
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += 4 * stride) {
+        PT x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                               // 4 independent loads in flight
+            const long long q = min(p + k * stride, np - 1);
+            x[k] = SOA ? __ldcs(p0 + q) : __ldcs(p0 + 3 * q);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long q = p + k * stride;
+            if (q >= np_pad) break;                                  // warp-uniform
+            const int d = q < np ? dest_rank<PT>(x[k], R) : -1;
+            if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;  // the usual case: nobody leaves
+            int head, offset, length;
+            warp_runs_r(d, lane, head, offset, length);
+            if (d >= 0 && offset == 0) atomicAdd(counts + d, (unsigned long long)length);
+        }
     }
 }
 
@@ -62,27 +93,37 @@ __global__ void route_scan_kernel(const unsigned long long *counts, int P, unsig
 template <typename PT, bool SOA, typename MT>
 __global__ void __launch_bounds__(256)
 route_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
-                     const MT *__restrict__ mass, long long np, double scale, int N, int ppr, int self,
+                     const MT *__restrict__ mass, long long np, RouteGeom R,
                      unsigned long long *__restrict__ cursor, long long capacity, PT *__restrict__ out_pos,
                      MT *__restrict__ out_mass) {
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long np_pad = (np + 31) & ~31LL;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += stride) {
-        int d = p < np ? dest_rank<PT, SOA>(p0, p, scale, N, ppr) : -1;
-        if (d == self) d = -1;
-        if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;
-        int head, offset, length;
-        warp_runs_r(d, lane, head, offset, length);
-        unsigned long long slot = 0;
-        if (d >= 0 && offset == 0) slot = atomicAdd(cursor + d, (unsigned long long)length);
-        slot = __shfl_sync(0xffffffffu, slot, head) + offset;
-        if (d >= 0 && (long long)slot < capacity) {
-            PT x, y, z;
-            if (SOA) { x = p0[p]; y = p1[p]; z = p2[p]; }
-            else     { x = p0[3 * p]; y = p0[3 * p + 1]; z = p0[3 * p + 2]; }
-            out_pos[3 * slot] = x; out_pos[3 * slot + 1] = y; out_pos[3 * slot + 2] = z;
-            if (mass) out_mass[slot] = mass[p];
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += 4 * stride) {
+        PT x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long q = min(p + k * stride, np - 1);
+            x[k] = SOA ? __ldcs(p0 + q) : __ldcs(p0 + 3 * q);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long q = p + k * stride;
+            if (q >= np_pad) break;
+            const int d = q < np ? dest_rank<PT>(x[k], R) : -1;
+            if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;
+            int head, offset, length;
+            warp_runs_r(d, lane, head, offset, length);
+            unsigned long long slot = 0;
+            if (d >= 0 && offset == 0) slot = atomicAdd(cursor + d, (unsigned long long)length);
+            slot = __shfl_sync(0xffffffffu, slot, head) + offset;
+            if (d >= 0 && (long long)slot < capacity) {
+                PT y, z;
+                if (SOA) { y = p1[q]; z = p2[q]; }
+                else     { y = p0[3 * q + 1]; z = p0[3 * q + 2]; }
+                out_pos[3 * slot] = x[k]; out_pos[3 * slot + 1] = y; out_pos[3 * slot + 2] = z;
+                if (mass) out_mass[slot] = mass[q];
+            }
         }
     }
 }
@@ -91,19 +132,22 @@ template <typename PT, bool SOA, typename MT>
 static int route_typed(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass, long long np,
                        double pos_scale, int nranks, unsigned long long *counts, long long capacity, void *out_pos,
                        void *out_mass, cudaStream_t st) {
-    const int ppr = P->N / nranks;
-    const int self = P->x0 / ppr;
-    const double scale = pos_scale * (double)P->N;
+    RouteGeom R;
+    R.N = P->N; R.ppr = P->N / nranks; R.self = P->x0 / R.ppr; R.x0 = P->x0;
+    R.scale = pos_scale * (double)P->N;
+    R.s0 = (float)R.scale;
+    R.s1 = (float)(R.scale - (double)R.s0);
+    R.s2 = (float)(R.scale - (double)R.s0 - (double)R.s1);
     unsigned long long *cursor = counts + nranks;
     APK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * nranks, st));
     if (np > 0) {
-        const int blocks = (int)std::min<long long>((np + 255) / 256, (long long)P->num_sms * 16);
-        route_count_kernel<PT, SOA><<<blocks, 256, 0, st>>>((const PT *)p0, np, scale, P->N, ppr, self, counts);
+        const int blocks = (int)std::min<long long>((np + 1023) / 1024, (long long)P->num_sms * 8);
+        route_count_kernel<PT, SOA><<<blocks, 256, 0, st>>>((const PT *)p0, np, R, counts);
         APK_CUDA(cudaGetLastError());
         route_scan_kernel<<<1, 32, 0, st>>>(counts, nranks, cursor);
         APK_CUDA(cudaGetLastError());
         route_scatter_kernel<PT, SOA, MT><<<blocks, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2,
-                                                                  (const MT *)mass, np, scale, P->N, ppr, self, cursor,
+                                                                  (const MT *)mass, np, R, cursor,
                                                                   capacity, (PT *)out_pos, (MT *)out_mass);
         APK_CUDA(cudaGetLastError());
     }
