@@ -314,3 +314,50 @@ def test_interlaced_pair_deposit_matches_two_deposits(ab, oracle_fast, resampler
             got = eng.store_mesh(mesh).cpu().numpy()
             np.testing.assert_allclose(got, want, rtol=0, atol=3e-6 * want.max())
             assert got.sum() == pytest.approx(want.sum(), rel=1e-6)
+
+
+def test_2048_mesh_64bit_indexing(ab):
+    """Size-independent properties at BASELINE's largest mesh: 2048^3 cells exceed 2^32 flat indices."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~80 GB of device memory")
+    from astrild_b200 import engine as _engine
+    N, L = 2048, 1000.0
+    eng = ab.PkEngine(N, L)
+    try:
+        # particles in the far corner: flat cell index ~ N^3 - 1 > 2^32
+        g = np.array([[N - 1.25, N - 1.5, N - 1.75], [0.25, 0.5, 0.75], [N / 2 + 0.5, N - 0.75, 3.25]])
+        pos = (g * L / N).astype(np.float64)
+        mass = np.array([2.0, 3.0, 5.0])
+        for method in ("atomic", "sorted"):
+            mesh = eng.deposit(pos, mass, "tsc", method=method)
+            assert eng.mesh_sum(mesh) == pytest.approx(10.0, rel=1e-6)
+            m = mesh.view(N, N, eng.ldz)
+            # TSC: the home cell of particle 0 is (N-1, N-1 or N-2.., ...): check one known weight product
+            w = lambda d: 0.75 - d * d                       # |d| <= 0.5
+            # particle 0: g = (N-1.25, N-1.5, N-1.75): home cells (N-1, N-1 [ties round up: floor(g+.5)=N-1], N-2)
+            hx, hy, hz = N - 1, N - 1, N - 2
+            dx, dy, dz = (N - 1.25) - hx, (N - 1.5) - hy, (N - 1.75) - hz
+            want = 2.0 * w(dx) * w(dy) * w(dz)
+            assert float(m[hx, hy, hz]) == pytest.approx(want, rel=1e-5)
+            del mesh, m
+        # mode counts of the whole 2048^3 lattice: every mode lands in exactly one bin
+        grid = torch.zeros((N, N, N // 2 + 1), dtype=torch.complex64, device="cuda")
+        res = eng.bin_power(eng.binning(kmin=2 * np.pi / L), grid)
+        assert int(res["Nsum"].sum()) == N ** 3
+        assert res["modes"][0] == 26 and len(res["modes"]) == N // 2 - 1
+        # r2c of a single plane wave at 2048^3 (cuFFT 64-bit plan): power only in its shell
+        del grid
+        mesh = eng.new_mesh()
+        x = torch.arange(N, device="cuda", dtype=torch.float32)
+        mesh.zero_()
+        mesh.view(N, N, eng.ldz)[:, :, :N] += torch.cos(2 * np.pi * 5 * x / N)[None, None, :]
+        c = eng.r2c(mesh)
+        res = eng.bin_power(eng.binning(kmin=2 * np.pi / L), c, scale=L ** 3 / float(N) ** 6)
+        b = 5 - 1
+        expect = 2 * (L ** 3 / 4) / res["modes"][b]
+        assert res["power"].real[b] == pytest.approx(expect, rel=1e-4)
+        assert np.abs(np.delete(res["power"].real, b)).max() < 1e-6 * expect
+    finally:
+        eng.close()
+        torch.cuda.empty_cache()
