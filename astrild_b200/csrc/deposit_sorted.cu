@@ -555,7 +555,10 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                     Moments<S, MASS> M;
                     M.clear();
                     const float fx = (float)cx, fy = (float)cy, fz = (float)(lane - OFF);
-                    for (int p = beg; p < end; ++p)
+                    // most cells hold 0-2 particles: peel two predicated iterations off the divergent loop
+                    if (beg < end) M.add(sx[beg] - fx, sy[beg] - fy, sz[beg] - fz, MASS ? sm[beg] : 1.f);
+                    if (beg + 1 < end) M.add(sx[beg + 1] - fx, sy[beg + 1] - fy, sz[beg + 1] - fz, MASS ? sm[beg + 1] : 1.f);
+                    for (int p = beg + 2; p < end; ++p)
                         M.add(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? sm[p] : 1.f);
                     // z-spread by shuffles.  Every lane owns exactly one tile cell (t = lane): it gets the
                     // middle weight of its own home cell plus the outer weights of its z-neighbours.  The
