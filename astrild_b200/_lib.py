@@ -41,6 +41,7 @@ SIGNATURES = {
     "apk_deposit": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _d, _i, _i, _vp, _vp],
     "apk_route_particles": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _vp, _i64, _vp, _vp, _vp],
     "apk_mesh_accumulate": [_vp, _vp, _vp, _i64, _vp],
+    "apk_slab_transpose_p2p": [_vp, _vp, _vp, _i64, _i, _vp],
     "apk_deposit_interlaced": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _i, _i, _vp, _vp, _vp],
     "apk_mesh_sum": [_vp, _vp, _i, _vp, _vp],
     "apk_padded_mesh_sum": [_vp, _vp, _vp, _vp],

@@ -30,6 +30,7 @@ int store_mesh_launch(apk_plan *, const float *, double, double *, cudaStream_t)
 int route_launch(apk_plan *, const void *, const void *, const void *, int, int, double, const void *, int, long long,
                  int, unsigned long long *, long long, void *, void *, cudaStream_t);
 int accumulate_launch(apk_plan *, float *, const float *, long long, cudaStream_t);
+int transpose_p2p_launch(apk_plan *, const void *, const unsigned long long *, long long, int, cudaStream_t);
 int bin_power_launch(apk_binning *, const void *, const void *, const void *, const void *, double *,
                      double *, double *, int64_t *, cudaStream_t);
 
@@ -253,6 +254,13 @@ int apk_route_particles(apk_plan *P, const void *p0, const void *p1, const void 
     DeviceGuard guard(P->device);
     return route_launch(P, p0, p1, p2, layout, pos_dtype, pos_scale, mass, mass_dtype, np, nranks,
                         (unsigned long long *)counts_dev, capacity, out_pos, out_mass, (cudaStream_t)stream);
+}
+
+int apk_slab_transpose_p2p(apk_plan *P, const void *grid, const uint64_t *peer_recv_dev, int64_t peer_offset_bytes,
+                           int nranks, void *stream) {
+    APK_REQUIRE(P && grid && peer_recv_dev, "apk_slab_transpose_p2p: null argument");
+    DeviceGuard guard(P->device);
+    return transpose_p2p_launch(P, grid, (const unsigned long long *)peer_recv_dev, peer_offset_bytes, nranks, (cudaStream_t)stream);
 }
 
 int apk_mesh_accumulate(apk_plan *P, float *dst, const float *src, int64_t n, void *stream) {

@@ -68,8 +68,6 @@ static BrickGrid make_brick_grid(const DepositGeom &G, int S) {
 }
 
 // home cell of a particle on one axis: floor(g) for CIC, floor(g + 0.5) for TSC / NGP
-template <int S>
-__device__ __forceinline__ double home_of(double g) { return (S == 2) ? floor(g) : floor(g + 0.5); }
 
 // floor(g) as double and as int32 without 64-bit conversion instructions (quarter-rate pipe):
 // adding 1.5*2^52 leaves rint(g) in the low word.  Valid for |g| < 2^31 grid units.

@@ -12,6 +12,7 @@
 #include "apk_common.cuh"
 #include "deposit_common.cuh"
 #include <algorithm>
+#include <cstdint>
 
 namespace apk {
 
@@ -166,6 +167,45 @@ int route_launch(apk_plan *P, const void *p0, const void *p1, const void *p2, in
                    : route_typed<float, false, float>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st);
     return soa ? route_typed<double, true, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st)
                : route_typed<double, false, double>(P, p0, p1, p2, mass, np, pos_scale, nranks, counts, capacity, out_pos, out_mass, st);
+}
+
+// ---- fused pack + peer store of the x <-> y slab transpose --------------------------------------------------
+// grid is complex64 [n0][N][nz] (x-slab of this rank).  For x_local and destination rank s, the ny*nz complex of
+// rows y in [s*ny, (s+1)*ny) are contiguous in the source AND in rank s's receive buffer [N][ny][nz] at
+// [x0 + x_local][0][0], so the transpose is n0*P contiguous chunk copies; they are written straight into the
+// peers' memory over NVLink (no pack pass, no NCCL staging).  One CTA works on one chunk at a time.
+template <typename V>
+__global__ void __launch_bounds__(256)
+transpose_p2p_kernel(const V *__restrict__ grid, const unsigned long long *__restrict__ peer_base, long long peer_off_bytes,
+                     int n0, int x0, int P, long long chunk_v /* V elements per chunk */, int rot) {
+    const long long nchunks = (long long)n0 * P;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const int xl = (int)(c / P);
+        const int s = (int)((c % P + rot) % P);                       // rank r starts with peer r: spreads the links
+        const V *src = grid + ((long long)xl * P + s) * chunk_v;
+        V *dst = reinterpret_cast<V *>(peer_base[s] + peer_off_bytes) + (long long)(x0 + xl) * chunk_v;
+        for (long long i = threadIdx.x; i < chunk_v; i += 4 * 256) {
+            V v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i + k * 256 < chunk_v) v[k] = __ldcs(src + i + k * 256);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) if (i + k * 256 < chunk_v) dst[i + k * 256] = v[k];
+        }
+    }
+}
+
+int transpose_p2p_launch(apk_plan *P, const void *grid, const unsigned long long *peer_base, long long peer_off_bytes,
+                         int nranks, cudaStream_t st) {
+    APK_REQUIRE(nranks >= 1 && P->N % nranks == 0 && P->n0 == P->N / nranks, "apk_slab_transpose_p2p: plan is not a 1/%d slab", nranks);
+    const long long chunk_bytes = (long long)(P->N / nranks) * P->Nk * 8;
+    const int rot = P->x0 / P->n0;
+    const int blocks = P->num_sms * 4;
+    if (chunk_bytes % 16 == 0 && ((uintptr_t)grid % 16) == 0 && peer_off_bytes % 16 == 0)
+        transpose_p2p_kernel<float4><<<blocks, 256, 0, st>>>((const float4 *)grid, peer_base, peer_off_bytes, P->n0, P->x0, nranks, chunk_bytes / 16, rot);
+    else
+        transpose_p2p_kernel<float2><<<blocks, 256, 0, st>>>((const float2 *)grid, peer_base, peer_off_bytes, P->n0, P->x0, nranks, chunk_bytes / 8, rot);
+    APK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 __global__ void __launch_bounds__(256) accumulate_kernel(float *__restrict__ dst, const float *__restrict__ src, long long n) {

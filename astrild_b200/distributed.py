@@ -24,6 +24,7 @@ gloo backend on CPUs -- that backend lives in tests/, never here.
 from __future__ import annotations
 
 import ctypes as ct
+import os
 
 import numpy as np
 import torch
@@ -103,6 +104,36 @@ class CudaSlabBackend:
         eng.ensure_workspace(0, False)
         _lib.call("apk_fft_c2c_1d", eng._plan, _ptr(grid), int(ny), eng.stream)
         return grid
+
+    # -- 5. transpose over NVLink peer memory -------------------------------------------------------
+    def setup_p2p(self, group, nfields: int) -> bool:
+        """Peer-mapped receive buffers (torch symmetric memory) for the fused pack + peer-store transpose.
+        Returns False (and the caller uses the NCCL all-to-all) if symmetric memory is unavailable."""
+        if getattr(self, "_p2p_fields", 0) >= nfields:
+            return self._p2p is not None
+        self._p2p, self._p2p_fields = None, nfields
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            ny, Nk = self.N // self.nranks, self.N // 2 + 1
+            buf = symm_mem.empty((nfields, self.N, ny, Nk), dtype=torch.complex64, device=self.device)
+            name = (group if group is not None else dist.group.WORLD).group_name
+            hdl = symm_mem.rendezvous(buf, name)
+            self._p2p = (buf, hdl)
+        except Exception as e:  # noqa: BLE001 -- any failure: keep the NCCL path
+            self._p2p_error = repr(e)
+            self._p2p = None
+        return self._p2p is not None
+
+    def transpose_p2p(self, grids: list) -> list:
+        buf, hdl = self._p2p
+        ny, Nk = self.N // self.nranks, self.N // 2 + 1
+        field_bytes = self.N * ny * Nk * 8
+        hdl.barrier(channel=0)                    # every rank is done reading the previous step's buffers
+        for f, g in enumerate(grids):
+            _lib.call("apk_slab_transpose_p2p", self.eng._plan, _ptr(g), ct.c_void_p(hdl.buffer_ptrs_dev),
+                      f * field_bytes, self.nranks, self.eng.stream)
+        hdl.barrier(channel=1)                    # every rank's blocks have landed
+        return [buf[f] for f in range(len(grids))]
 
     # -- 7. binning ----------------------------------------------------------------------------------
     def make_binning(self, y0: int, ny: int, kmin, dk, kmax, compensation, interlaced):
@@ -190,6 +221,7 @@ class SlabPk:
         self.eng = getattr(backend, "eng", None)
         self.ghost_lo, self.ghost_hi = 1, 2
         self.profile, self.last_profile = False, {}
+        self.p2p = os.environ.get("APK_SLAB_P2P", "1") != "0"     # fused peer-store transpose (falls back to NCCL)
         if self.P > 1 and self.n0 < 2:
             raise AstrildPkError("each rank needs at least 2 mesh planes")
 
@@ -276,7 +308,17 @@ class SlabPk:
         #    pipelined per field: while field f is packed and exchanged on a side stream, the 2-D FFT of
         #    field f+1 (and later the 1-D FFT of field f-1) runs on the main stream
         side = getattr(be, "side_stream", None)
-        if side is None or P == 1 or len(owned) == 1:
+        use_p2p = (P > 1 and self.p2p and isinstance(self.comm, TorchDistComm) and hasattr(be, "setup_p2p")
+                   and be.setup_p2p(self.comm.group, 2 if self.interlaced else 1))
+        if use_p2p:
+            grids = [be.fft2d(o) for o in owned]
+            mark("fft2d")
+            grids = be.transpose_p2p(grids)
+            del owned
+            mark("transpose")
+            grids = [be.fft1d(g, self.ny) for g in grids]
+            mark("fft1d")
+        elif side is None or P == 1 or len(owned) == 1:
             grids = [be.fft2d(o) for o in owned]
             mark("fft2d")
             grids = self._transpose(grids)

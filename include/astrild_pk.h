@@ -110,6 +110,15 @@ int apk_route_particles(apk_plan *plan, const void *p0, const void *p1, const vo
                         int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
                         int nranks, uint64_t *counts_dev, int64_t capacity, void *out_pos, void *out_mass,
                         void *stream);
+/* Fused pack + peer store of the x<->y slab transpose (step 5 of the distributed r2c) over NVLink peer
+ * memory: the block (x_local, y in rank s's range) of `grid` (complex64 [n0][N][N/2+1], output of
+ * apk_fft_r2c_2d) is written straight into rank s's receive buffer [N][N/nranks][N/2+1] at
+ * [x0 + x_local][y_local][z].  peer_recv_dev: DEVICE array of nranks base addresses (uint64) of the ranks'
+ * peer-mapped receive buffers (cuMem/IPC-mapped symmetric allocations); peer_offset_bytes is added to
+ * each (field offset).  The caller brackets the call with cross-rank barriers.  Replaces pfft's MPI
+ * transpose (PFFT_TRANSPOSED_OUT), which astrild never reaches on more than one rank.                */
+int apk_slab_transpose_p2p(apk_plan *plan, const void *grid, const uint64_t *peer_recv_dev,
+                           int64_t peer_offset_bytes, int nranks, void *stream);
 /* dst[i] += src[i], i < n: adds received ghost planes into the owned slab                       */
 int apk_mesh_accumulate(apk_plan *plan, float *dst, const float *src, int64_t n, void *stream);
 
