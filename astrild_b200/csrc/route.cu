@@ -55,11 +55,15 @@ __device__ __forceinline__ int dest_rank(const PT x, const RouteGeom &R) {
     return cell / R.ppr;
 }
 
-// pass 1: how many of my particles belong to each OTHER rank (the ones that stay are not touched:
-// the slab deposit skips particles it does not own, so only leavers are copied and sent)
-template <typename PT, bool SOA>
+// pass 1 (the only pass over all particles; reads x alone): particles that leave this slab are counted per
+// destination and staged in arrival order; the ones that stay are not touched (the slab deposit skips
+// particles it does not own, so the caller deposits its arrays as they are)
+template <typename PT, bool SOA, typename MT>
 __global__ void __launch_bounds__(256)
-route_count_kernel(const PT *__restrict__ p0, long long np, RouteGeom R, unsigned long long *__restrict__ counts) {
+route_stage_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
+                   const MT *__restrict__ mass, long long np, RouteGeom R, unsigned long long *__restrict__ counts,
+                   unsigned long long *__restrict__ total, long long capacity, PT *__restrict__ stage_pos,
+                   MT *__restrict__ stage_mass) {
     const int lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long np_pad = (np + 31) & ~31LL;
@@ -75,10 +79,21 @@ route_count_kernel(const PT *__restrict__ p0, long long np, RouteGeom R, unsigne
             const long long q = p + k * stride;
             if (q >= np_pad) break;                                  // warp-uniform
             const int d = q < np ? dest_rank<PT>(x[k], R) : -1;
-            if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;  // the usual case: nobody leaves
+            const unsigned int leaving = __ballot_sync(0xffffffffu, d >= 0);
+            if (leaving == 0u) continue;                             // the usual case: nobody leaves
             int head, offset, length;
             warp_runs_r(d, lane, head, offset, length);
             if (d >= 0 && offset == 0) atomicAdd(counts + d, (unsigned long long)length);
+            unsigned long long slot = 0;
+            if (lane == __ffs(leaving) - 1) slot = atomicAdd(total, (unsigned long long)__popc(leaving));
+            slot = __shfl_sync(0xffffffffu, slot, __ffs(leaving) - 1) + __popc(leaving & ((1u << lane) - 1u));
+            if (d >= 0 && (long long)slot < capacity) {
+                PT y, z;
+                if (SOA) { y = p1[q]; z = p2[q]; }
+                else     { y = p0[3 * q + 1]; z = p0[3 * q + 2]; }
+                stage_pos[3 * slot] = x[k]; stage_pos[3 * slot + 1] = y; stage_pos[3 * slot + 2] = z;
+                if (mass) stage_mass[slot] = mass[q];
+            }
         }
     }
 }
@@ -91,41 +106,21 @@ __global__ void route_scan_kernel(const unsigned long long *counts, int P, unsig
     }
 }
 
-template <typename PT, bool SOA, typename MT>
+// pass 2 (over the staged leavers only): group them by destination rank
+template <typename PT, typename MT>
 __global__ void __launch_bounds__(256)
-route_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
-                     const MT *__restrict__ mass, long long np, RouteGeom R,
-                     unsigned long long *__restrict__ cursor, long long capacity, PT *__restrict__ out_pos,
-                     MT *__restrict__ out_mass) {
-    const int lane = threadIdx.x & 31;
+route_group_kernel(const PT *__restrict__ stage_pos, const MT *__restrict__ stage_mass, const unsigned long long *__restrict__ total,
+                   long long capacity, RouteGeom R, unsigned long long *__restrict__ cursor, PT *__restrict__ out_pos,
+                   MT *__restrict__ out_mass) {
+    const long long n = min((long long)*total, capacity);
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long np_pad = (np + 31) & ~31LL;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np_pad; p += 4 * stride) {
-        PT x[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long q = min(p + k * stride, np - 1);
-            x[k] = SOA ? __ldcs(p0 + q) : __ldcs(p0 + 3 * q);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long q = p + k * stride;
-            if (q >= np_pad) break;
-            const int d = q < np ? dest_rank<PT>(x[k], R) : -1;
-            if (__ballot_sync(0xffffffffu, d >= 0) == 0u) continue;
-            int head, offset, length;
-            warp_runs_r(d, lane, head, offset, length);
-            unsigned long long slot = 0;
-            if (d >= 0 && offset == 0) slot = atomicAdd(cursor + d, (unsigned long long)length);
-            slot = __shfl_sync(0xffffffffu, slot, head) + offset;
-            if (d >= 0 && (long long)slot < capacity) {
-                PT y, z;
-                if (SOA) { y = p1[q]; z = p2[q]; }
-                else     { y = p0[3 * q + 1]; z = p0[3 * q + 2]; }
-                out_pos[3 * slot] = x[k]; out_pos[3 * slot + 1] = y; out_pos[3 * slot + 2] = z;
-                if (mass) out_mass[slot] = mass[q];
-            }
-        }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const PT x = stage_pos[3 * i];
+        int d = dest_rank<PT>(x, R);
+        if (d < 0) continue;                                         // cannot happen: staged particles leave
+        const unsigned long long slot = atomicAdd(cursor + d, 1ULL);
+        out_pos[3 * slot] = x; out_pos[3 * slot + 1] = stage_pos[3 * i + 1]; out_pos[3 * slot + 2] = stage_pos[3 * i + 2];
+        if (stage_mass) out_mass[slot] = stage_mass[i];
     }
 }
 
@@ -140,16 +135,25 @@ static int route_typed(apk_plan *P, const void *p0, const void *p1, const void *
     R.s1 = (float)(R.scale - (double)R.s0);
     R.s2 = (float)(R.scale - (double)R.s0 - (double)R.s1);
     unsigned long long *cursor = counts + nranks;
+    // staging lives in the plan workspace (the deposit that follows reuses it)
+    const size_t need = (size_t)capacity * (3 * sizeof(PT) + (mass ? sizeof(MT) : 0)) + 64;
+    APK_REQUIRE(capacity == 0 || (P->workspace && P->workspace_bytes >= need),
+                "apk_route_particles: %zu workspace bytes needed for staging, %zu set", need, P->workspace_bytes);
+    unsigned long long *total = (unsigned long long *)P->workspace;
+    PT *stage_pos = (PT *)((char *)P->workspace + 64);
+    MT *stage_mass = mass ? (MT *)(stage_pos + 3 * (size_t)capacity) : nullptr;
     APK_CUDA(cudaMemsetAsync(counts, 0, sizeof(unsigned long long) * nranks, st));
-    if (np > 0) {
+    if (np > 0 && capacity > 0) {
+        APK_CUDA(cudaMemsetAsync(total, 0, sizeof(unsigned long long), st));
         const int blocks = (int)std::min<long long>((np + 1023) / 1024, (long long)P->num_sms * 8);
-        route_count_kernel<PT, SOA><<<blocks, 256, 0, st>>>((const PT *)p0, np, R, counts);
+        route_stage_kernel<PT, SOA, MT><<<blocks, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, (const MT *)mass,
+                                                               np, R, counts, total, capacity, stage_pos, stage_mass);
         APK_CUDA(cudaGetLastError());
         route_scan_kernel<<<1, 32, 0, st>>>(counts, nranks, cursor);
         APK_CUDA(cudaGetLastError());
-        route_scatter_kernel<PT, SOA, MT><<<blocks, 256, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2,
-                                                                  (const MT *)mass, np, R, cursor,
-                                                                  capacity, (PT *)out_pos, (MT *)out_mass);
+        const int gblocks = (int)std::min<long long>((capacity + 255) / 256, (long long)P->num_sms * 4);
+        route_group_kernel<PT, MT><<<gblocks, 256, 0, st>>>(stage_pos, stage_mass, total, capacity, R, cursor,
+                                                            (PT *)out_pos, (MT *)out_mass);
         APK_CUDA(cudaGetLastError());
     }
     return 0;

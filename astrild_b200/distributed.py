@@ -55,8 +55,9 @@ class CudaSlabBackend:
         if mass is not None:
             m = eng._to_device(mass).to(dt).contiguous()
         code = _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64
-        capacity = max(1 << 16, npart // 8)
+        capacity = min(max(npart, 1), max(1 << 16, npart // 8))
         while True:
+            eng.ensure_workspace(max(npart, capacity), m is not None)   # the leavers are staged in the plan workspace
             out_pos = torch.empty((capacity, 3), dtype=dt, device=self.device)
             out_mass = torch.empty(capacity, dtype=dt, device=self.device) if m is not None else None
             _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),

@@ -104,7 +104,9 @@ int apk_deposit_interlaced(apk_plan *plan, const void *p0, const void *p1, const
  * out_pos (masses, same dtype, into out_mass when mass != NULL), grouped by destination rank;
  * counts_dev[0..nranks) receives the per-destination counts (uint64, own rank = 0; the array must
  * hold 2*nranks entries, the second half is scratch).  At most `capacity` particles are written:
- * the host compares sum(counts) with capacity and retries with a larger buffer if needed.
+ * the host compares sum(counts) with capacity and retries with a larger buffer if needed.  One pass
+ * over the particles (x only); the leavers are staged in the plan workspace, which must hold
+ * capacity * (3 + [mass]) * sizeof(dtype) + 64 bytes.
  * pmesh equivalent: ParticleMesh.decompose + layout.exchange (unused by astrild).               */
 int apk_route_particles(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout,
                         int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
