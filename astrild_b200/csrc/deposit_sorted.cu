@@ -8,7 +8,7 @@
 // traffic is real but not credited.
 //
 // Pipeline (all on one stream, no host sync):
-//   1. brick_count_kernel   every particle -> key of the brick (12 x 12 x 30 home cells for TSC, 12 x 12 x 31
+//   1. brick_count_kernel   every particle -> key of the brick (12 x 6 x 30 home cells for TSC, 12 x 6 x 31
 //                           for CIC) that holds its HOME cell; per-brick counts with one RED per warp-run of
 //                           equal keys (snapshot order is spatially coherent).  float32 positions use an
 //                           error-free float32 product (no FP64 issue slots), float64 positions the oracle's
@@ -19,18 +19,19 @@
 //                           3 floats (+ mass), contiguously.  One read and one write of the particles replace a
 //                           multi-pass radix sort; order inside a brick is arbitrary (the deposit does not care).
 //      PAIR mode (apk_deposit_interlaced): one partition serves both interlaced meshes -- particles whose
-//      two home cells fall in different bricks (~11 %) are filed twice, sign bits of the payload say which
+//      two home cells fall in different bricks are filed twice, sign bits of the payload say which
 //      mesh a copy is for.
-//   4. brick_deposit_kernel persistent CTAs pull bricks from a counter; per brick and per chunk of <= CH
-//      particles: counting-sort the chunk by home cell inside shared memory (native 32-bit ATOMS.ADD gives each
-//      particle its rank), then one thread per home cell sums the S^3 window moments of its own particles in
-//      registers (packed FFMA2).  The moments are spread WITHOUT atomics (shared-memory float atomics are CAS
-//      loops on sm_100): the 32 lanes of a warp are the 32 tile cells of one (x,y) column along z (30 home
-//      cells + 2 halo lanes for TSC), so the z-spread is two warp shuffles with no edge cases, and the
-//      (x,y)-spread is a plain load/add/store into the shared tile that is conflict-free because the 16
-//      columns active at a time are 3 cells apart in x and y (9 colour classes, one __syncthreads each).
-//      The finished 14 x 14 x 32 (TSC) tile is added to the mesh with RED.ADD.V2.F32 on aligned pairs,
-//      skipping zeros; bricks are visited x-major so neighbouring tiles meet in L2.
+//   4. brick_deposit_kernel persistent CTAs (8 warps, 3 per SM) pull bricks from a counter; per brick and per
+//      chunk of <= CH particles: counting-sort the chunk by home cell inside shared memory (native 32-bit
+//      ATOMS.ADD gives each particle its rank), then one thread per home cell sums the S^3 window moments of
+//      its own particles in registers (packed FFMA2).  The moments are spread WITHOUT atomics and WITHOUT
+//      shared memory (shared-memory float atomics are CAS loops on sm_100): every warp owns a 3 x 3 block of
+//      (x,y) columns, its 32 lanes are the 32 cells of a column along z (30 home cells + 2 halo lanes for
+//      TSC), so the z-spread is two warp shuffles with no edge cases and the (x,y)-spread is an add into the
+//      warp's 5 x 5 (TSC) window of registers with compile-time indices.  No barrier separates the columns:
+//      warps run through their 9 columns independently.  The window then goes to the mesh as one coalesced
+//      128-byte RED.ADD.F32 per (x,y) column, zeros skipped; bricks are visited x-major so neighbouring
+//      windows meet in L2.
 #include "apk_common.cuh"
 #include "deposit_common.cuh"
 #include <algorithm>
@@ -39,14 +40,16 @@
 
 namespace apk {
 
-constexpr int BX = 12, BY = 12;                 // brick edge in cells along x, y (multiples of 3)
+constexpr int BX = 12, BY = 6;                  // brick edge in cells along x, y (multiples of 3)
 constexpr int BZ = 32;                          // z-lanes of a column = tile cells along z (one warp)
 // home cells along z: 32 - (S-1), so that a column's 32 lanes are exactly its 32 tile cells
 // (30 home cells + 2 halo lanes for TSC, 31 + 1 for CIC) and the spread needs no halo special case
 template <int S> struct BrickZ { static constexpr int CELLS = BZ - (S - 1); };
-constexpr int BRICK_CELLS = BX * BY * BZ;       // 4608 count slots (halo lanes stay empty)
-constexpr int DEP_THREADS = 512;                // 16 warps = 16 columns of one colour class
-constexpr int CH = 5120;                        // particles per shared-memory chunk
+constexpr int BRICK_CELLS = BX * BY * BZ;       // 2304 count slots (halo lanes stay empty)
+constexpr int DEP_THREADS = 256;                // 8 warps, each owns a 3 x 3 block of (x,y) columns
+constexpr int DEP_CTAS_PER_SM = 3;              // 24 warps per SM at <= 85 registers
+constexpr int CH = 3072;                        // particles per shared-memory chunk
+static_assert(DEP_THREADS / 32 == (BX / 3) * (BY / 3), "one warp per 3 x 3 block of columns");
 constexpr int PPT = CH / DEP_THREADS;           // particles per thread per chunk
 
 struct P3 { float x, y, z; };
@@ -337,26 +340,14 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
     }
 }
 
-template <int S>
-struct TileDims {
-    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ;
-    static constexpr int SIZE = TX * TY * TZ;
-};
-
 // dynamic shared memory layout of brick_deposit_kernel
-template <int S, bool MASS>
+template <bool MASS>
 struct DepSmem {
-    static constexpr int tile_floats = TileDims<S>::SIZE;
     static constexpr int cnt_ints = BRICK_CELLS + 1;
-    static constexpr size_t bytes = sizeof(float) * tile_floats + sizeof(int) * (cnt_ints + 64) +
-                                    sizeof(float) * CH * (MASS ? 4 : 3) + 64;
+    static constexpr size_t bytes = sizeof(int) * (cnt_ints + 64) + sizeof(float) * CH * (MASS ? 4 : 3) + 64;
 };
 
-__device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
-}
-
-// Window moments of the particles [beg, end) of one home cell, accumulated with packed FFMA2.
+// Window moments of the particles of one home cell, accumulated with packed FFMA2.
 // Layout: A[a][c] = float2 over the b-pair (first, last) of the window, Bm[a][c] = middle b (TSC only).
 template <int S, bool MASS>
 struct Moments {
@@ -424,14 +415,12 @@ __device__ __forceinline__ bool unpack_pair(VT &v, int sel) {
 }
 
 template <int S, bool MASS, typename VT>
-__global__ void __launch_bounds__(DEP_THREADS, 2)
+__global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM)
 brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
                      DepositGeom G, BrickGrid B, unsigned int *__restrict__ work_counter,
                      float *__restrict__ mesh, int sel) {
-    using TD = TileDims<S>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *tile = reinterpret_cast<float *>(smem_raw);
-    int *cnt = reinterpret_cast<int *>(tile + TD::SIZE);          // [BRICK_CELLS + 1]
+    int *cnt = reinterpret_cast<int *>(smem_raw);                 // [BRICK_CELLS + 1]
     int *wsum = cnt + BRICK_CELLS + 1;                            // [64] scan scratch
     float *sx = reinterpret_cast<float *>(wsum + 64);
     float *sy = sx + CH;
@@ -442,8 +431,12 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    constexpr int OFF = (S == 3) ? 1 : 0;   // tile origin = brick origin - OFF
-    constexpr int HALF = PPT / 2;
+    constexpr int OFF = (S == 3) ? 1 : 0;   // window origin = home cell - OFF
+    constexpr int NBATCH = 3, BATCH = PPT / NBATCH;   // loads are issued BATCH at a time before first use
+    static_assert(BATCH * NBATCH == PPT, "PPT must divide into the load batches");
+    constexpr int W = 3 + S - 1;            // edge of a warp's private window: its 3 columns + halo
+    // this warp's 3 x 3 block of (x,y) columns inside the brick
+    const int bi = warp / (BY / 3), bj = warp % (BY / 3);
 
     for (;;) {
         __syncthreads();
@@ -454,43 +447,47 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
         const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
         if (pbeg == pend) continue;
 
-        for (int i = tid; i < TD::SIZE; i += DEP_THREADS) tile[i] = 0.f;
+        const int bz = brick % B.nbz;
+        const int by = (brick / B.nbz) % B.nby;
+        const int bx = brick / (B.nbz * B.nby);
 
         for (unsigned int c0 = pbeg; c0 < pend; c0 += CH) {
             const int nchunk = (int)min((unsigned int)CH, pend - c0);
+            if (c0 != pbeg) __syncthreads();   // every warp is done with the previous chunk's lists
             for (int i = tid; i <= BRICK_CELLS; i += DEP_THREADS) cnt[i] = 0;
-            __syncthreads();   // also orders the tile zeroing / previous chunk's spreading
+            __syncthreads();
 
             // ---- rank my particles inside their home cell (cell | rank << 13 kept in a register;
-            //      the coordinates are re-read from L1/L2 in the scatter pass to stay <= 64 regs).
-            //      Loads are issued in two batches before first use to overlap their latency.
+            //      the coordinates are re-read from L1/L2 in the scatter pass to save registers).
+            //      Loads are issued in batches before first use to overlap their latency.
             int packed[PPT];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                VT v[HALF];
+            for (int h = 0; h < NBATCH; ++h) {
+                VT v[BATCH];
 #pragma unroll
-                for (int k = 0; k < HALF; ++k) {
-                    const int i = (h * HALF + k) * DEP_THREADS + tid;
+                for (int k = 0; k < BATCH; ++k) {
+                    const int i = (h * BATCH + k) * DEP_THREADS + tid;
                     v[k] = vals[c0 + min(i, nchunk - 1)];
                 }
 #pragma unroll
-                for (int k = 0; k < HALF; ++k) {
-                    const int i = (h * HALF + k) * DEP_THREADS + tid;
+                for (int k = 0; k < BATCH; ++k) {
+                    const int i = (h * BATCH + k) * DEP_THREADS + tid;
                     const bool keep = unpack_pair(v[k], sel);
                     int hx, hy, hz;
                     if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
                     else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
                     hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BrickZ<S>::CELLS - 1));
                     const int cell = (hx * BY + hy) * BZ + hz + OFF;          // z-lane = home z + OFF
-                    packed[h * HALF + k] = -1;
-                    if (i < nchunk && keep) packed[h * HALF + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
+                    packed[h * BATCH + k] = -1;
+                    if (i < nchunk && keep) packed[h * BATCH + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
                 }
             }
             __syncthreads();
 
-            // ---- exclusive scan of the 4608 cell counts (9 per thread) -------------------
+            // ---- exclusive scan of the cell counts (9 per thread) ------------------------
             {
-                constexpr int PER = BRICK_CELLS / DEP_THREADS;   // 9
+                constexpr int PER = BRICK_CELLS / DEP_THREADS;
+                static_assert(PER * DEP_THREADS == BRICK_CELLS, "cells must divide evenly among the threads");
                 int v[PER], s = 0;
 #pragma unroll
                 for (int k = 0; k < PER; ++k) { v[k] = cnt[tid * PER + k]; s += v[k]; }
@@ -522,16 +519,16 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
 
             // ---- scatter into cell order --------------------------------------------------
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                VT v[HALF];
+            for (int h = 0; h < NBATCH; ++h) {
+                VT v[BATCH];
 #pragma unroll
-                for (int k = 0; k < HALF; ++k) {
-                    const int i = (h * HALF + k) * DEP_THREADS + tid;
+                for (int k = 0; k < BATCH; ++k) {
+                    const int i = (h * BATCH + k) * DEP_THREADS + tid;
                     v[k] = vals[c0 + min(i, nchunk - 1)];
                 }
 #pragma unroll
-                for (int k = 0; k < HALF; ++k) {
-                    const int pk = packed[h * HALF + k];
+                for (int k = 0; k < BATCH; ++k) {
+                    const int pk = packed[h * BATCH + k];
                     if (pk >= 0) {
                         unpack_pair(v[k], sel);
                         const int slot = cnt[pk & 8191] + (pk >> 13);
@@ -542,28 +539,33 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
             }
             __syncthreads();
 
-            // ---- moments per home cell, conflict-free spreading, 9 colour classes --------
-#pragma unroll 1
-            for (int cls = 0; cls < 9; ++cls) {
-                const int cx = 3 * (warp >> 2) + cls / 3;
-                const int cy = 3 * (warp & 3) + cls % 3;
-                const int cell = (cx * BY + cy) * BZ + lane;              // lane = tile z index = home z + OFF
-                const int beg = cnt[cell], end = cnt[cell + 1];
-                if (__ballot_sync(0xffffffffu, end > beg) != 0u) {
+            // ---- moments per home cell; each warp walks its own 9 columns, no CTA barrier ----
+            // lane = z-cell of the column (home z + OFF), so the z-spread is two shuffles: every lane
+            // gets the middle weight of its own home cell plus the outer weights of its z-neighbours
+            // (halo lanes have no home cell; CIC: lane 0 must drop its wrapped-around 'up').  The
+            // (x,y)-spread is a register add into the warp's window, static indices throughout.
+            //      The window (one z-cell per lane) lives in registers during this phase only, so that it
+            //      does not add to the register pressure of the sort phases above.
+            float R[W][W];
+#pragma unroll
+            for (int u = 0; u < W; ++u)
+#pragma unroll
+                for (int v = 0; v < W; ++v) R[u][v] = 0.f;
+            const float up_on = (S == 2 && lane == 0) ? 0.f : 1.f;
+            const float fz = (float)(lane - OFF);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int cx = 3 * bi + i, cy = 3 * bj + j;
+                    const int cell = (cx * BY + cy) * BZ + lane;
+                    const int beg = cnt[cell], end = cnt[cell + 1];
+                    if (__ballot_sync(0xffffffffu, end > beg) == 0u) continue;
                     Moments<S, MASS> M;
                     M.clear();
-                    const float fx = (float)cx, fy = (float)cy, fz = (float)(lane - OFF);
-                    // most cells hold 0-2 particles: peel two predicated iterations off the divergent loop
-                    if (beg < end) M.add(sx[beg] - fx, sy[beg] - fy, sz[beg] - fz, MASS ? sm[beg] : 1.f);
-                    if (beg + 1 < end) M.add(sx[beg + 1] - fx, sy[beg + 1] - fy, sz[beg + 1] - fz, MASS ? sm[beg + 1] : 1.f);
-                    for (int p = beg + 2; p < end; ++p)
+                    const float fx = (float)cx, fy = (float)cy;
+                    for (int p = beg; p < end; ++p)
                         M.add(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? sm[p] : 1.f);
-                    // z-spread by shuffles.  Every lane owns exactly one tile cell (t = lane): it gets the
-                    // middle weight of its own home cell plus the outer weights of its z-neighbours.  The
-                    // halo lanes (TSC: 0 and 31, CIC: 31) have no home cell, so their moments are zero and
-                    // the shuffles need no edge masks (CIC: lane 0 must drop its wrapped-around 'up').
-                    float *col = tile + (cx * TD::TY + cy) * TD::TZ + lane;
-                    const float up_on = (S == 2 && lane == 0) ? 0.f : 1.f;
 #pragma unroll
                     for (int a = 0; a < S; ++a)
 #pragma unroll
@@ -576,56 +578,25 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                                 const float dn = __shfl_down_sync(0xffffffffu, M.get(a, b, 0), 1);
                                 own = M.get(a, b, S / 2) + up + dn;
                             }
-                            col[(a * TD::TY + b) * TD::TZ] += own;
+                            R[i + a][j + b] += own;
                         }
                 }
-                __syncthreads();
             }
-        }
 
-        // ---- add the tile to the mesh: one warp per (x,y) row, RED.ADD.V2.F32 on aligned pairs ----
-        const int bz = brick % B.nbz;
-        const int by = (brick / B.nbz) % B.nby;
-        const int bx = brick / (B.nbz * B.nby);
-        const int gz0 = bz * BrickZ<S>::CELLS - OFF;       // global z of tile index 0
-        const bool fast_z = gz0 >= 0 && gz0 + TD::TZ <= G.N && (G.N & 1) == 0;
-        // rows of this warp: r = warp + 16 j; lane j prepares row j's mesh offset (-1: skip)
-        constexpr int ROWS = TD::TX * TD::TY, WARPS = DEP_THREADS / 32;
-        long long my_off = -1;
-        {
-            const int r = warp + WARPS * lane;
-            if (r < ROWS) {
-                const int tx = r / TD::TY, ty = r - tx * TD::TY;
-                int px = bx * BX - OFF + tx;
+            // ---- add the warp's window to the mesh: one coalesced RED per (x,y) column ----
+            const int gz = wrap_index32(bz * BrickZ<S>::CELLS - OFF + lane, G.N);
+            const int x0 = bx * BX + 3 * bi - OFF, y0 = by * BY + 3 * bj - OFF;
+#pragma unroll
+            for (int u = 0; u < W; ++u) {
+                int px = x0 + u;
                 bool ok = true;
                 if (G.slab) ok = px >= 0 && px < G.nplanes;
                 else px = wrap_index32(px, G.N);
-                const int gy = wrap_index32(by * BY - OFF + ty, G.N);
-                if (ok) my_off = ((long long)px * G.N + gy) * G.ldz;
-            }
-        }
-        for (int j = 0; warp + WARPS * j < ROWS; ++j) {
-            const long long off = __shfl_sync(0xffffffffu, my_off, j);
-            if (off < 0) continue;
-            float *grow = mesh + off;
-            const float *trow = tile + (warp + WARPS * j) * TD::TZ;
-            if (fast_z) {
-                // aligned pairs (global z even) go out as RED.ADD.V2.F32; if the row starts on an odd z its
-                // first and last cells are single
-                const int first = gz0 & 1;
-                if (lane < 16 - first) {
-                    const int t = first + 2 * lane;
-                    const float v0 = trow[t], v1 = trow[t + 1];
-                    if (v0 != 0.f || v1 != 0.f) red_add_v2(grow + gz0 + t, v0, v1);
-                } else if (first && lane >= 30) {
-                    const int t = lane == 30 ? 0 : 31;
-                    const float v = trow[t];
-                    if (v != 0.f) atomicAdd(grow + gz0 + t, v);
-                }
-            } else {
-                for (int tz = lane; tz < TD::TZ; tz += 32) {
-                    const float v = trow[tz];
-                    if (v != 0.f) atomicAdd(grow + wrap_index32(gz0 + tz, G.N), v);
+                float *plane = mesh + (long long)px * G.N * G.ldz + gz;
+#pragma unroll
+                for (int v = 0; v < W; ++v) {
+                    const int gy = wrap_index32(y0 + v, G.N);
+                    if (ok && R[u][v] != 0.f) atomicAdd(plane + (long long)gy * G.ldz, R[u][v]);
                 }
             }
         }
@@ -685,7 +656,7 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
 
     auto kern = brick_deposit_kernel<S, MASS, VT>;
-    const size_t smem = DepSmem<S, MASS>::bytes;
+    const size_t smem = DepSmem<MASS>::bytes;
     APK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     APK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEP_THREADS, smem));
