@@ -165,6 +165,46 @@ __device__ __forceinline__ unsigned int f32_finish(const AxisBase &a, float t32,
     return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
 }
 
+// Both interlaced twins at once (mesh 0: shift folded into t32, mesh 1: half a cell further).  The twin's home
+// cell is the same cell or the next one along each axis, so its brick and brick-local coordinate follow from
+// mesh 0's with a compare instead of a second floor / wrap / divide.
+template <int S>
+__device__ __forceinline__ void f32_finish_pair(const AxisBase &a, float t32, const DepositGeom &G, const BrickGrid &B,
+                                                unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3],
+                                                bool &far) {
+    if (!a.owned) { key0 = key1 = 0xffffffffu; return; }
+    int b0[3], b1[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float f = a.f[d] + t32;
+        const float c = floorf(f);
+        f -= c;                                      // [0, 1)
+        const bool up = f >= 0.5f;                   // the twin's home cell is the next one
+        const float f1 = up ? f - 0.5f : f + 0.5f;
+        int hl = wrap_near((int)(a.h[d] + c), G.N, far);
+        int lim = G.N;
+        if (d == 0 && G.slab) {
+            hl -= G.plane0;
+            hl += (hl < 0) ? G.N : 0;
+            hl -= (hl >= G.N) ? G.N : 0;
+            hl = (hl >= G.nplanes) ? 0 : hl;
+            lim = G.nplanes;
+        }
+        const int edge = d == 0 ? BX : (d == 1 ? BY : BrickZ<S>::CELLS);
+        const int b = hl / edge;
+        const int loc = hl - b * edge;
+        b0[d] = b;
+        l0[d] = ((S == 2) ? f : f - 0.5f) + (float)loc;
+        int loc1 = loc + (up ? 1 : 0), bb = b;
+        if (loc1 == edge) { loc1 = 0; bb = b + 1; }
+        if (hl + (up ? 1 : 0) >= lim) { loc1 = 0; bb = 0; }      // periodic wrap (slab planes: unreachable for owned)
+        b1[d] = bb;
+        l1[d] = ((S == 2) ? f1 : f1 - 0.5f) + (float)loc1;
+    }
+    key0 = (unsigned int)((b0[0] * B.nby + b0[1]) * B.nbz + b0[2]);
+    key1 = (unsigned int)((b1[0] * B.nby + b1[1]) * B.nbz + b1[2]);
+}
+
 // keys and brick-local coordinates of one particle for mesh 0 (G) and, if PAIR, its interlaced twin (G1)
 template <int S, typename PT, bool PAIR>
 __device__ __forceinline__ void brick_keys(const PT *x, const DepositGeom &G, const DepositGeom &G1, const BrickGrid &B,
@@ -173,9 +213,12 @@ __device__ __forceinline__ void brick_keys(const PT *x, const DepositGeom &G, co
         if (G.t32 >= 0.f && (!PAIR || G1.t32 >= 0.f)) {
             bool far = false;                        // position more than a box length outside the box (rare)
             const AxisBase a = f32_base(x, G, far);
-            key0 = f32_finish<S>(a, G.t32, G, B, l0, far);
-            key1 = key0;
-            if (PAIR) key1 = f32_finish<S>(a, G1.t32, G1, B, l1, far);
+            if (PAIR) {
+                f32_finish_pair<S>(a, G.t32, G, B, key0, l0, key1, l1, far);
+            } else {
+                key0 = f32_finish<S>(a, G.t32, G, B, l0, far);
+                key1 = key0;
+            }
             if (!far) return;
         }
     }
@@ -254,16 +297,12 @@ brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const P
     }
 }
 
-// exclusive scan of counts[0..n) -> start[0..n], cursor[0..n) = start; one CTA (n is ~10^4..10^6)
-__global__ void __launch_bounds__(1024)
-brick_scan_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *__restrict__ start,
-                  unsigned int *__restrict__ cursor) {
-    __shared__ unsigned int wsum[32];
+// exclusive scan of counts[0..n) -> start[0..n], cursor[0..n) = start, in two launches of n / SCAN_SEG CTAs:
+// per-segment totals, then every CTA sums the totals below it and scans its own segment (n is 10^4..10^7)
+constexpr int SCAN_PER = 8, SCAN_SEG = 1024 * SCAN_PER;
+
+__device__ __forceinline__ unsigned int block_exclusive_scan_1024(unsigned int s, unsigned int *wsum, unsigned int &total) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = (n + 1023) / 1024;
-    const int a = min(tid * per, n), b = min(a + per, n);
-    unsigned int s = 0;
-    for (int i = a; i < b; ++i) s += counts[i];
     unsigned int incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -281,11 +320,42 @@ brick_scan_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *
             if (lane >= o) wi += t;
         }
         wsum[lane] = wi - w;
+        if (lane == 31) wsum[32] = wi;
     }
     __syncthreads();
-    unsigned int run = wsum[warp] + incl - s;
-    for (int i = a; i < b; ++i) { start[i] = run; cursor[i] = run; run += counts[i]; }
-    if (tid == 1023) start[n] = run;
+    total = wsum[32];
+    const unsigned int excl = wsum[warp] + incl - s;
+    __syncthreads();
+    return excl;
+}
+
+__global__ void __launch_bounds__(1024)
+brick_segsum_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *__restrict__ seg_total) {
+    __shared__ unsigned int wsum[33];
+    const int a = min(blockIdx.x * SCAN_SEG + threadIdx.x * SCAN_PER, n), b = min(a + SCAN_PER, n);
+    unsigned int s = 0;
+    for (int i = a; i < b; ++i) s += counts[i];
+    unsigned int total;
+    block_exclusive_scan_1024(s, wsum, total);
+    if (threadIdx.x == 0) seg_total[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024)
+brick_scan_kernel(const unsigned int *__restrict__ counts, int n, const unsigned int *__restrict__ seg_total,
+                  unsigned int *__restrict__ start, unsigned int *__restrict__ cursor) {
+    __shared__ unsigned int wsum[33];
+    unsigned int below = 0, base, total;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) below += seg_total[i];
+    block_exclusive_scan_1024(below, wsum, base);       // base = sum of the segments below this one
+    const int a = min(blockIdx.x * SCAN_SEG + threadIdx.x * SCAN_PER, n), b = min(a + SCAN_PER, n);
+    unsigned int v[SCAN_PER], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) { v[k] = a + k < b ? counts[a + k] : 0u; s += v[k]; }
+    unsigned int run = base + block_exclusive_scan_1024(s, wsum, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k)
+        if (a + k < b) { start[a + k] = run; cursor[a + k] = run; run += v[k]; }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) start[n] = base + total;
 }
 
 // PAIR payload: u + 1 per axis, u = unshifted coordinate relative to the brick origin (>= -1); the sign
@@ -361,10 +431,10 @@ struct Moments {
             for (int c = 0; c < S; ++c) { A[a][c] = make_float2(0.f, 0.f); Bm[a][c] = 0.f; }
     }
 
-    __device__ __forceinline__ void add(float dx, float dy, float dz, float m) {
-        float wx[S], wz[S];
-        float2 wyp;          // (first, last) y weights
-        float wym = 0.f;     // middle y weight (TSC)
+    // per-axis window weights of one particle: x and z as scalars, y packed as (first, last) + middle
+    __device__ __forceinline__ static void weights(float dx, float dy, float dz, float m, float (&wx)[S],
+                                                   float2 &wyp, float &wym, float (&wz)[S]) {
+        wym = 0.f;
         if (S == 2) {
             wx[0] = 1.f - dx; wx[S - 1] = dx;
             wz[0] = 1.f - dz; wz[S - 1] = dz;
@@ -383,6 +453,12 @@ struct Moments {
 #pragma unroll
             for (int a = 0; a < S; ++a) wx[a] *= m;
         }
+    }
+
+    __device__ __forceinline__ void add(float dx, float dy, float dz, float m) {
+        float wx[S], wz[S], wym;
+        float2 wyp;
+        weights(dx, dy, dz, m, wx, wyp, wym, wz);
 #pragma unroll
         for (int a = 0; a < S; ++a) {
             const float2 wxy = __fmul2_rn(make_float2(wx[a], wx[a]), wyp);
@@ -391,6 +467,25 @@ struct Moments {
             for (int c = 0; c < S; ++c) {
                 A[a][c] = __ffma2_rn(wxy, make_float2(wz[c], wz[c]), A[a][c]);
                 if (S == 3) Bm[a][c] = fmaf(wxm, wz[c], Bm[a][c]);
+            }
+        }
+    }
+
+    // the first particle of a cell sets the moments (no zeroing pass); !valid: the cell is empty, all zero.
+    // The coordinates of an empty cell are whatever the list holds at that slot, hence the selects.
+    __device__ __forceinline__ void init(float dx, float dy, float dz, float m, bool valid) {
+        float wx[S], wz[S], wym;
+        float2 wyp;
+        weights(valid ? dx : 0.f, valid ? dy : 0.f, valid ? dz : 0.f, m, wx, wyp, wym, wz);
+#pragma unroll
+        for (int a = 0; a < S; ++a) {
+            const float w = valid ? wx[a] : 0.f;
+            const float2 wxy = __fmul2_rn(make_float2(w, w), wyp);
+            const float wxm = w * wym;
+#pragma unroll
+            for (int c = 0; c < S; ++c) {
+                A[a][c] = __fmul2_rn(wxy, make_float2(wz[c], wz[c]));
+                Bm[a][c] = (S == 3) ? wxm * wz[c] : 0.f;
             }
         }
     }
@@ -562,9 +657,13 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                     const int beg = cnt[cell], end = cnt[cell + 1];
                     if (__ballot_sync(0xffffffffu, end > beg) == 0u) continue;
                     Moments<S, MASS> M;
-                    M.clear();
                     const float fx = (float)cx, fy = (float)cy;
-                    for (int p = beg; p < end; ++p)
+                    {
+                        const bool any = end > beg;
+                        const int p = any ? beg : 0;
+                        M.init(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? (any ? sm[p] : 0.f) : 1.f, any);
+                    }
+                    for (int p = beg + 1; p < end; ++p)
                         M.add(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? sm[p] : 1.f);
 #pragma unroll
                     for (int a = 0; a < S; ++a)
@@ -584,20 +683,22 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
             }
 
             // ---- add the warp's window to the mesh: one coalesced RED per (x,y) column ----
+            //      (offsets of the W planes and W rows are formed once, 64-bit: 2048^3 meshes exceed 2^32 cells)
             const int gz = wrap_index32(bz * BrickZ<S>::CELLS - OFF + lane, G.N);
             const int x0 = bx * BX + 3 * bi - OFF, y0 = by * BY + 3 * bj - OFF;
+            long long row[W];
+#pragma unroll
+            for (int v = 0; v < W; ++v) row[v] = (long long)wrap_index32(y0 + v, G.N) * G.ldz + gz;
 #pragma unroll
             for (int u = 0; u < W; ++u) {
                 int px = x0 + u;
                 bool ok = true;
                 if (G.slab) ok = px >= 0 && px < G.nplanes;
                 else px = wrap_index32(px, G.N);
-                float *plane = mesh + (long long)px * G.N * G.ldz + gz;
+                float *plane = mesh + (long long)px * G.N * G.ldz;
 #pragma unroll
-                for (int v = 0; v < W; ++v) {
-                    const int gy = wrap_index32(y0 + v, G.N);
-                    if (ok && R[u][v] != 0.f) atomicAdd(plane + (long long)gy * G.ldz, R[u][v]);
-                }
+                for (int v = 0; v < W; ++v)
+                    if (ok && R[u][v] != 0.f) atomicAdd(plane + row[v], R[u][v]);
             }
         }
     }
@@ -612,7 +713,8 @@ static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int pair) {
     if (np <= 0) return 0;
     const size_t vs = with_mass ? sizeof(P4) : sizeof(P3);
-    return align256(vs * (size_t)np * (pair ? 2 : 1)) + 3 * align256(4 * (max_bricks(P) + 2)) + 256;
+    return align256(vs * (size_t)np * (pair ? 2 : 1)) + 3 * align256(4 * (max_bricks(P) + 2)) +
+           align256(4 * (max_bricks(P) / SCAN_SEG + 2)) + 256;
 }
 
 // mesh1 != nullptr: interlaced pair -- G is the shift-0 geometry, mesh1 gets the shift-0.5 twin
@@ -638,6 +740,7 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     unsigned int *counts = (unsigned int *)w; w += tab;
     unsigned int *brick_start = (unsigned int *)w; w += tab;
     unsigned int *cursor = (unsigned int *)w; w += tab;
+    unsigned int *seg_total = (unsigned int *)w; w += align256(4 * (max_bricks(P) / SCAN_SEG + 2));
     unsigned int *counter = (unsigned int *)w;
 
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
@@ -647,7 +750,10 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     brick_count_kernel<S, PT, SOA, PAIR><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, G1, B, counts);
     APK_CUDA(cudaGetLastError());
     P->mark(1, st);
-    brick_scan_kernel<<<1, 1024, 0, st>>>(counts, B.nbricks, brick_start, cursor);
+    const int nseg = (B.nbricks + SCAN_SEG - 1) / SCAN_SEG;
+    brick_segsum_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total);
+    APK_CUDA(cudaGetLastError());
+    brick_scan_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total, brick_start, cursor);
     APK_CUDA(cudaGetLastError());
     P->mark(2, st);
     brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT><<<pb, PART_THREADS, 0, st>>>(
