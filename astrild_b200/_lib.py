@@ -9,7 +9,8 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libastrild_pk.so")
+# ASTRILD_PK_LIB: path of another build of the same library (kernel A/B measurements)
+LIB_PATH = os.environ.get("ASTRILD_PK_LIB") or os.path.join(_HERE, "lib", "libastrild_pk.so")
 
 APK_F32, APK_F64 = 0, 1
 APK_AOS, APK_SOA = 0, 1

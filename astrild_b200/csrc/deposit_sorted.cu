@@ -47,7 +47,10 @@ constexpr int BZ = 32;                          // z-lanes of a column = tile ce
 template <int S> struct BrickZ { static constexpr int CELLS = BZ - (S - 1); };
 constexpr int BRICK_CELLS = BX * BY * BZ;       // 2304 count slots (halo lanes stay empty)
 constexpr int DEP_THREADS = 256;                // 8 warps, each owns a 3 x 3 block of (x,y) columns
-constexpr int DEP_CTAS_PER_SM = 3;              // 24 warps per SM at <= 85 registers
+#ifndef APK_DEP_CTAS
+#define APK_DEP_CTAS 3
+#endif
+constexpr int DEP_CTAS_PER_SM = APK_DEP_CTAS;   // 3: 24 warps per SM at <= 85 registers
 constexpr int CH = 3072;                        // particles per shared-memory chunk
 static_assert(DEP_THREADS / 32 == (BX / 3) * (BY / 3), "one warp per 3 x 3 block of columns");
 constexpr int PPT = CH / DEP_THREADS;           // particles per thread per chunk
@@ -140,69 +143,54 @@ __device__ __forceinline__ AxisBase f32_base(const float *x, const DepositGeom &
     return a;
 }
 
-template <int S>
-__device__ __forceinline__ unsigned int f32_finish(const AxisBase &a, float t32, const DepositGeom &G,
-                                                   const BrickGrid &B, float (&l)[3], bool &far) {
-    if (!a.owned) return 0xffffffffu;
-    int b[3];
+// Home cell, brick and brick-local coordinate of mesh 0 (shift folded into t32) and, if PAIR, of its interlaced
+// twin half a cell further.  Everything stays in float32 registers -- cell and brick indices are small integers,
+// exact in float -- so one axis costs ~25 FP32 instructions and no integer division; the brick index is
+// floor((cell + 0.5) / edge), whose argument is never closer than 1/(2 edge) to an integer.  The twin's home
+// cell is the same cell or the next one along each axis, so its brick and brick-local coordinate follow from
+// mesh 0's with compares instead of a second floor / wrap / divide.  Needs nbricks < 2^24 (else: float64 path).
+template <int S, bool PAIR>
+__device__ __forceinline__ void f32_finish(const AxisBase &a, float t32, const DepositGeom &G, const BrickGrid &B,
+                                           unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3],
+                                           bool &far) {
+    if (!a.owned) { key0 = key1 = 0xffffffffu; return; }
+    const float Nf = (float)G.N;
+    float b0[3], b1[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         float f = a.f[d] + t32;                      // + shift (+ 0.5: TSC rounds to the nearest cell)
         const float c = floorf(f);
         f -= c;                                      // [0, 1)
-        const float frac = (S == 2) ? f : f - 0.5f;  // relative to the home cell
-        int hl = wrap_near((int)(a.h[d] + c), G.N, far);
-        if (d == 0 && G.slab) {
-            hl -= G.plane0;
-            hl += (hl < 0) ? G.N : 0;
-            hl -= (hl >= G.N) ? G.N : 0;
-            hl = (hl >= G.nplanes) ? 0 : hl;
+        float h = a.h[d] + c;                        // home cell, within one box length of the box
+        h = h >= Nf ? h - Nf : h;
+        h = h < 0.f ? h + Nf : h;
+        far |= !(h >= 0.f && h < Nf);
+        float lim = Nf;
+        if (d == 0 && G.slab) {                      // local plane index of a slab plan
+            h -= (float)G.plane0;
+            h = h < 0.f ? h + Nf : h;
+            h = h >= Nf ? h - Nf : h;
+            lim = (float)G.nplanes;
+            h = h >= lim ? 0.f : h;                  // unreachable for owned particles
         }
-        const int edge = d == 0 ? BX : (d == 1 ? BY : BrickZ<S>::CELLS);
-        b[d] = hl / edge;
-        l[d] = frac + (float)(hl - b[d] * edge);
-    }
-    return (unsigned int)((b[0] * B.nby + b[1]) * B.nbz + b[2]);
-}
-
-// Both interlaced twins at once (mesh 0: shift folded into t32, mesh 1: half a cell further).  The twin's home
-// cell is the same cell or the next one along each axis, so its brick and brick-local coordinate follow from
-// mesh 0's with a compare instead of a second floor / wrap / divide.
-template <int S>
-__device__ __forceinline__ void f32_finish_pair(const AxisBase &a, float t32, const DepositGeom &G, const BrickGrid &B,
-                                                unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3],
-                                                bool &far) {
-    if (!a.owned) { key0 = key1 = 0xffffffffu; return; }
-    int b0[3], b1[3];
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        float f = a.f[d] + t32;
-        const float c = floorf(f);
-        f -= c;                                      // [0, 1)
-        const bool up = f >= 0.5f;                   // the twin's home cell is the next one
-        const float f1 = up ? f - 0.5f : f + 0.5f;
-        int hl = wrap_near((int)(a.h[d] + c), G.N, far);
-        int lim = G.N;
-        if (d == 0 && G.slab) {
-            hl -= G.plane0;
-            hl += (hl < 0) ? G.N : 0;
-            hl -= (hl >= G.N) ? G.N : 0;
-            hl = (hl >= G.nplanes) ? 0 : hl;
-            lim = G.nplanes;
-        }
-        const int edge = d == 0 ? BX : (d == 1 ? BY : BrickZ<S>::CELLS);
-        const int b = hl / edge;
-        const int loc = hl - b * edge;
+        const float edge = d == 0 ? (float)BX : (d == 1 ? (float)BY : (float)BrickZ<S>::CELLS);
+        const float b = floorf(fmaf(h, 1.f / edge, 0.5f / edge));
+        const float loc = fmaf(-edge, b, h);         // cell inside the brick
         b0[d] = b;
-        l0[d] = ((S == 2) ? f : f - 0.5f) + (float)loc;
-        int loc1 = loc + (up ? 1 : 0), bb = b;
-        if (loc1 == edge) { loc1 = 0; bb = b + 1; }
-        if (hl + (up ? 1 : 0) >= lim) { loc1 = 0; bb = 0; }      // periodic wrap (slab planes: unreachable for owned)
-        b1[d] = bb;
-        l1[d] = ((S == 2) ? f1 : f1 - 0.5f) + (float)loc1;
+        l0[d] = ((S == 2) ? f : f - 0.5f) + loc;
+        if (PAIR) {
+            const bool up = f >= 0.5f;               // the twin's home cell is the next one
+            const float one = up ? 1.f : 0.f;
+            float loc1 = loc + one, bb = b;
+            if (loc1 == edge) { loc1 = 0.f; bb = b + 1.f; }
+            if (h + one >= lim) { loc1 = 0.f; bb = 0.f; }          // periodic wrap (slab planes: unreachable)
+            b1[d] = bb;
+            l1[d] = ((S == 2) ? f - 0.5f * one + 0.5f * (1.f - one) : f - one) + loc1;
+        }
     }
-    key0 = (unsigned int)((b0[0] * B.nby + b0[1]) * B.nbz + b0[2]);
-    key1 = (unsigned int)((b1[0] * B.nby + b1[1]) * B.nbz + b1[2]);
+    key0 = (unsigned int)(int)fmaf(fmaf(b0[0], (float)B.nby, b0[1]), (float)B.nbz, b0[2]);
+    key1 = key0;
+    if (PAIR) key1 = (unsigned int)(int)fmaf(fmaf(b1[0], (float)B.nby, b1[1]), (float)B.nbz, b1[2]);
 }
 
 // keys and brick-local coordinates of one particle for mesh 0 (G) and, if PAIR, its interlaced twin (G1)
@@ -210,15 +198,10 @@ template <int S, typename PT, bool PAIR>
 __device__ __forceinline__ void brick_keys(const PT *x, const DepositGeom &G, const DepositGeom &G1, const BrickGrid &B,
                                            unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3]) {
     if constexpr (std::is_same<PT, float>::value) {
-        if (G.t32 >= 0.f && (!PAIR || G1.t32 >= 0.f)) {
+        if (G.t32 >= 0.f && (!PAIR || G1.t32 >= 0.f) && B.nbricks < (1 << 24)) {
             bool far = false;                        // position more than a box length outside the box (rare)
             const AxisBase a = f32_base(x, G, far);
-            if (PAIR) {
-                f32_finish_pair<S>(a, G.t32, G, B, key0, l0, key1, l1, far);
-            } else {
-                key0 = f32_finish<S>(a, G.t32, G, B, l0, far);
-                key1 = key0;
-            }
+            f32_finish<S, PAIR>(a, G.t32, G, B, key0, l0, key1, l1, far);
             if (!far) return;
         }
     }
@@ -360,8 +343,11 @@ brick_scan_kernel(const unsigned int *__restrict__ counts, int n, const unsigned
 
 // PAIR payload: u + 1 per axis, u = unshifted coordinate relative to the brick origin (>= -1); the sign
 // of x says "not for mesh 0", the sign of y "not for mesh 1".
+#ifndef APK_SCATTER_MIN_CTAS
+#define APK_SCATTER_MIN_CTAS 3
+#endif
 template <int S, typename PT, bool SOA, bool MASS, bool PAIR, typename VT>
-__global__ void __launch_bounds__(PART_THREADS)
+__global__ void __launch_bounds__(PART_THREADS, APK_SCATTER_MIN_CTAS)
 brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
                      const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, DepositGeom G1,
                      BrickGrid B, unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
@@ -375,37 +361,53 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
         const long long first = base + threadIdx.x;
         const Raw4<PT> cur = nxt;
         if (base + step < np) load4<PT, SOA>(p0, p1, p2, first + step, PART_THREADS, np, nxt);   // next tile in flight
+        // Software pipeline of depth one: item k claims its slots (returning atomics, ~600 cycles) and item k-1,
+        // whose slots have arrived meanwhile, is stored.
+        VT pv = {}, pw = {};
+        unsigned int pslot = 0, pslot1 = 0;
+        int phead = 0, poffset = 0;
+        bool plive = false, pextra = false;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const long long p = first + (long long)k * PART_THREADS;
-            float l[3], l1[3];
-            unsigned int key, key1;
-            brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1);
-            if (p >= np) key = 0xffffffffu;
-            VT v;
-            v.x = l[0]; v.y = l[1]; v.z = l[2];
-            if constexpr (MASS) {
-                const long long pc = min(p, np - 1);
-                v.m = mass_f64 ? (float)((const double *)mass)[pc] : ((const float *)mass)[pc];
-            }
-            if constexpr (PAIR) {
-                v.x = fmaxf(l[0] + 1.f, 0.f); v.y = fmaxf(l[1] + 1.f, 0.f); v.z = fmaxf(l[2] + 1.f, 0.f);
-                if (key1 != key) v.y = -v.y;                     // first copy is mesh-0-only
-            }
-            int head, offset, length;
-            warp_runs(key, lane, head, offset, length);
-            unsigned int slot = 0;
-            if (key != 0xffffffffu && offset == 0) slot = atomicAdd(cursor + key, (unsigned int)length);
-            slot = __shfl_sync(0xffffffffu, slot, head) + offset;
-            if (key != 0xffffffffu) vals[slot] = v;
-            if constexpr (PAIR) {
-                const bool extra = key != 0xffffffffu && key1 != key;
-                if (__any_sync(0xffffffffu, extra) && extra) {   // second copy: mesh-1-only, in mesh 1's brick
-                    VT w = v;
-                    w.x = -fmaxf(l1[0] + 0.5f, 0.f); w.y = fmaxf(l1[1] + 0.5f, 0.f); w.z = fmaxf(l1[2] + 0.5f, 0.f);
-                    vals[atomicAdd(cursor + key1, 1u)] = w;
+        for (int k = 0; k <= 4; ++k) {
+            VT v = {}, w = {};
+            unsigned int slot = 0, slot1 = 0;
+            int head = 0, offset = 0, length = 0;
+            bool live = false, extra = false;
+            if (k < 4) {
+                const long long p = first + (long long)k * PART_THREADS;
+                float l[3], l1[3];
+                unsigned int key, key1;
+                brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1);
+                if (p >= np) key = 0xffffffffu;
+                live = key != 0xffffffffu;
+                v.x = l[0]; v.y = l[1]; v.z = l[2];
+                if constexpr (MASS) {
+                    const long long pc = min(p, np - 1);
+                    v.m = mass_f64 ? (float)((const double *)mass)[pc] : ((const float *)mass)[pc];
+                }
+                if constexpr (PAIR) {
+                    v.x = fmaxf(l[0] + 1.f, 0.f); v.y = fmaxf(l[1] + 1.f, 0.f); v.z = fmaxf(l[2] + 1.f, 0.f);
+                    if (key1 != key) v.y = -v.y;                     // first copy is mesh-0-only
+                }
+                warp_runs(key, lane, head, offset, length);
+                if (live && offset == 0) slot = atomicAdd(cursor + key, (unsigned int)length);
+                if constexpr (PAIR) {
+                    extra = live && key1 != key;
+                    if (extra) {                                     // second copy: mesh-1-only, in mesh 1's brick
+                        w = v;
+                        w.x = -fmaxf(l1[0] + 0.5f, 0.f); w.y = fmaxf(l1[1] + 0.5f, 0.f); w.z = fmaxf(l1[2] + 0.5f, 0.f);
+                        slot1 = atomicAdd(cursor + key1, 1u);
+                    }
                 }
             }
+            if (k > 0) {
+                const unsigned int ps = __shfl_sync(0xffffffffu, pslot, phead) + poffset;
+                if (plive) vals[ps] = pv;
+                if constexpr (PAIR) {
+                    if (pextra) vals[pslot1] = pw;
+                }
+            }
+            pv = v; pw = w; pslot = slot; pslot1 = slot1; phead = head; poffset = offset; plive = live; pextra = extra;
         }
     }
 }
@@ -521,7 +523,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     float *sy = sx + CH;
     float *sz = sy + CH;
     float *sm = sz + CH;                                          // only if MASS
-    __shared__ unsigned int s_brick;
+    __shared__ unsigned int s_info[3];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -533,14 +535,32 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     // this warp's 3 x 3 block of (x,y) columns inside the brick
     const int bi = warp / (BY / 3), bj = warp % (BY / 3);
 
+    // Work queue: thread 0 claims the NEXT brick while the current one is processed.  The three dependent
+    // round trips (counter, then the brick's particle range) are spread over the sort phases so that no warp
+    // waits for them: the counter is read at the top, the range after the rank phase, and both are published
+    // in s_info before the moments phase.
+    if (tid == 0) {
+        const unsigned int b0 = atomicAdd(work_counter, 1u);
+        s_info[0] = b0;
+        s_info[1] = b0 < (unsigned)B.nbricks ? brick_start[b0] : 0u;
+        s_info[2] = b0 < (unsigned)B.nbricks ? brick_start[b0 + 1] : 0u;
+    }
+
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_brick = atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const unsigned int brick = s_brick;
+        const unsigned int brick = s_info[0], pbeg = s_info[1], pend = s_info[2];
         if (brick >= (unsigned)B.nbricks) break;
-        const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
-        if (pbeg == pend) continue;
+        unsigned int nb = 0, nbeg = 0, nend = 0;
+        if (tid == 0) nb = atomicAdd(work_counter, 1u);
+        if (pbeg == pend) {            // empty brick: publish the next one right away
+            __syncthreads();
+            if (tid == 0) {
+                s_info[0] = nb;
+                s_info[1] = nb < (unsigned)B.nbricks ? brick_start[nb] : 0u;
+                s_info[2] = nb < (unsigned)B.nbricks ? brick_start[nb + 1] : 0u;
+            }
+            continue;
+        }
 
         const int bz = brick % B.nbz;
         const int by = (brick / B.nbz) % B.nby;
@@ -578,6 +598,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 }
             }
             __syncthreads();
+            if (tid == 0 && c0 == pbeg && nb < (unsigned)B.nbricks) { nbeg = brick_start[nb]; nend = brick_start[nb + 1]; }
 
             // ---- exclusive scan of the cell counts (9 per thread) ------------------------
             {
@@ -632,6 +653,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                     }
                 }
             }
+            if (tid == 0 && c0 == pbeg) { s_info[0] = nb; s_info[1] = nbeg; s_info[2] = nend; }
             __syncthreads();
 
             // ---- moments per home cell; each warp walks its own 9 columns, no CTA barrier ----
@@ -640,7 +662,8 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
             // (halo lanes have no home cell; CIC: lane 0 must drop its wrapped-around 'up').  The
             // (x,y)-spread is a register add into the warp's window, static indices throughout.
             //      The window (one z-cell per lane) lives in registers during this phase only, so that it
-            //      does not add to the register pressure of the sort phases above.
+            //      does not add to the register pressure of the sort phases above.  (A rolled loop over i
+            //      with a sliding window of S planes has a third of the code and measured 3 % slower.)
             float R[W][W];
 #pragma unroll
             for (int u = 0; u < W; ++u)
@@ -682,13 +705,12 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 }
             }
 
-            // ---- add the warp's window to the mesh: one coalesced RED per (x,y) column ----
-            //      (offsets of the W planes and W rows are formed once, 64-bit: 2048^3 meshes exceed 2^32 cells)
+            // ---- add the warp's window to the mesh: one coalesced 128-byte RED per (x,y) column ----
             const int gz = wrap_index32(bz * BrickZ<S>::CELLS - OFF + lane, G.N);
             const int x0 = bx * BX + 3 * bi - OFF, y0 = by * BY + 3 * bj - OFF;
-            long long row[W];
+            int row[W];                 // offset of (y0 + v, gz) inside a plane: < N * ldz, fits 32 bits
 #pragma unroll
-            for (int v = 0; v < W; ++v) row[v] = (long long)wrap_index32(y0 + v, G.N) * G.ldz + gz;
+            for (int v = 0; v < W; ++v) row[v] = wrap_index32(y0 + v, G.N) * G.ldz + gz;
 #pragma unroll
             for (int u = 0; u < W; ++u) {
                 int px = x0 + u;
