@@ -313,32 +313,42 @@ __device__ __forceinline__ unsigned int block_exclusive_scan_1024(unsigned int s
 }
 
 __global__ void __launch_bounds__(1024)
-brick_segsum_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *__restrict__ seg_total) {
+brick_segsum_kernel(const unsigned int *__restrict__ counts, int n, unsigned int *__restrict__ seg_total,
+                    unsigned int *__restrict__ seg_filled) {
     __shared__ unsigned int wsum[33];
     const int a = min(blockIdx.x * SCAN_SEG + threadIdx.x * SCAN_PER, n), b = min(a + SCAN_PER, n);
-    unsigned int s = 0;
-    for (int i = a; i < b; ++i) s += counts[i];
-    unsigned int total;
+    unsigned int s = 0, f = 0;
+    for (int i = a; i < b; ++i) { const unsigned int c = counts[i]; s += c; f += c != 0u; }
+    unsigned int total, filled;
     block_exclusive_scan_1024(s, wsum, total);
-    if (threadIdx.x == 0) seg_total[blockIdx.x] = total;
+    block_exclusive_scan_1024(f, wsum, filled);
+    if (threadIdx.x == 0) { seg_total[blockIdx.x] = total; seg_filled[blockIdx.x] = filled; }
 }
 
+// also lists the non-empty bricks (filled[0..nfilled), ascending) so that the deposit kernel never visits an
+// empty one: slab plans, halo catalogues and the particles received from other ranks leave most bricks empty
 __global__ void __launch_bounds__(1024)
 brick_scan_kernel(const unsigned int *__restrict__ counts, int n, const unsigned int *__restrict__ seg_total,
-                  unsigned int *__restrict__ start, unsigned int *__restrict__ cursor) {
+                  const unsigned int *__restrict__ seg_filled, unsigned int *__restrict__ start,
+                  unsigned int *__restrict__ cursor, unsigned int *__restrict__ filled, unsigned int *__restrict__ nfilled) {
     __shared__ unsigned int wsum[33];
-    unsigned int below = 0, base, total;
-    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) below += seg_total[i];
+    unsigned int below = 0, fbelow = 0, base, fbase, total, ftotal;
+    for (int i = threadIdx.x; i < (int)blockIdx.x; i += 1024) { below += seg_total[i]; fbelow += seg_filled[i]; }
     block_exclusive_scan_1024(below, wsum, base);       // base = sum of the segments below this one
+    block_exclusive_scan_1024(fbelow, wsum, fbase);
     const int a = min(blockIdx.x * SCAN_SEG + threadIdx.x * SCAN_PER, n), b = min(a + SCAN_PER, n);
-    unsigned int v[SCAN_PER], s = 0;
+    unsigned int v[SCAN_PER], s = 0, f = 0;
 #pragma unroll
-    for (int k = 0; k < SCAN_PER; ++k) { v[k] = a + k < b ? counts[a + k] : 0u; s += v[k]; }
+    for (int k = 0; k < SCAN_PER; ++k) { v[k] = a + k < b ? counts[a + k] : 0u; s += v[k]; f += v[k] != 0u; }
     unsigned int run = base + block_exclusive_scan_1024(s, wsum, total);
+    unsigned int frun = fbase + block_exclusive_scan_1024(f, wsum, ftotal);
 #pragma unroll
     for (int k = 0; k < SCAN_PER; ++k)
-        if (a + k < b) { start[a + k] = run; cursor[a + k] = run; run += v[k]; }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) start[n] = base + total;
+        if (a + k < b) {
+            start[a + k] = run; cursor[a + k] = run; run += v[k];
+            if (v[k] != 0u) filled[frun++] = (unsigned int)(a + k);
+        }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) { start[n] = base + total; *nfilled = fbase + ftotal; }
 }
 
 // PAIR payload: u + 1 per axis, u = unshifted coordinate relative to the brick origin (>= -1); the sign
@@ -514,6 +524,7 @@ __device__ __forceinline__ bool unpack_pair(VT &v, int sel) {
 template <int S, bool MASS, typename VT>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM)
 brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
+                     const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
                      DepositGeom G, BrickGrid B, unsigned int *__restrict__ work_counter,
                      float *__restrict__ mesh, int sel) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -535,12 +546,14 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     // this warp's 3 x 3 block of (x,y) columns inside the brick
     const int bi = warp / (BY / 3), bj = warp % (BY / 3);
 
-    // Work queue: thread 0 claims the NEXT brick while the current one is processed.  The three dependent
-    // round trips (counter, then the brick's particle range) are spread over the sort phases so that no warp
-    // waits for them: the counter is read at the top, the range after the rank phase, and both are published
-    // in s_info before the moments phase.
+    // Work queue over the list of non-empty bricks: thread 0 claims the NEXT entry while the current brick is
+    // processed.  The dependent round trips (queue counter -> brick id -> the brick's particle range) are
+    // spread over the sort phases so that no warp waits for them; the result is published in s_info before
+    // the moments phase.
+    const unsigned int nfilled = *nfilled_ptr;
     if (tid == 0) {
-        const unsigned int b0 = atomicAdd(work_counter, 1u);
+        const unsigned int i0 = atomicAdd(work_counter, 1u);
+        const unsigned int b0 = i0 < nfilled ? filled[i0] : (unsigned)B.nbricks;
         s_info[0] = b0;
         s_info[1] = b0 < (unsigned)B.nbricks ? brick_start[b0] : 0u;
         s_info[2] = b0 < (unsigned)B.nbricks ? brick_start[b0 + 1] : 0u;
@@ -550,17 +563,8 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
         __syncthreads();
         const unsigned int brick = s_info[0], pbeg = s_info[1], pend = s_info[2];
         if (brick >= (unsigned)B.nbricks) break;
-        unsigned int nb = 0, nbeg = 0, nend = 0;
-        if (tid == 0) nb = atomicAdd(work_counter, 1u);
-        if (pbeg == pend) {            // empty brick: publish the next one right away
-            __syncthreads();
-            if (tid == 0) {
-                s_info[0] = nb;
-                s_info[1] = nb < (unsigned)B.nbricks ? brick_start[nb] : 0u;
-                s_info[2] = nb < (unsigned)B.nbricks ? brick_start[nb + 1] : 0u;
-            }
-            continue;
-        }
+        unsigned int ni = 0, nb = (unsigned)B.nbricks, nbeg = 0, nend = 0;
+        if (tid == 0) ni = atomicAdd(work_counter, 1u);
 
         const int bz = brick % B.nbz;
         const int by = (brick / B.nbz) % B.nby;
@@ -598,7 +602,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 }
             }
             __syncthreads();
-            if (tid == 0 && c0 == pbeg && nb < (unsigned)B.nbricks) { nbeg = brick_start[nb]; nend = brick_start[nb + 1]; }
+            if (tid == 0 && c0 == pbeg && ni < nfilled) nb = filled[ni];
 
             // ---- exclusive scan of the cell counts (9 per thread) ------------------------
             {
@@ -632,6 +636,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 if (tid == DEP_THREADS - 1) cnt[BRICK_CELLS] = run;
             }
             __syncthreads();
+            if (tid == 0 && c0 == pbeg && nb < (unsigned)B.nbricks) { nbeg = brick_start[nb]; nend = brick_start[nb + 1]; }
 
             // ---- scatter into cell order --------------------------------------------------
 #pragma unroll
@@ -735,8 +740,8 @@ static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int pair) {
     if (np <= 0) return 0;
     const size_t vs = with_mass ? sizeof(P4) : sizeof(P3);
-    return align256(vs * (size_t)np * (pair ? 2 : 1)) + 3 * align256(4 * (max_bricks(P) + 2)) +
-           align256(4 * (max_bricks(P) / SCAN_SEG + 2)) + 256;
+    return align256(vs * (size_t)np * (pair ? 2 : 1)) + 4 * align256(4 * (max_bricks(P) + 2)) +
+           2 * align256(4 * (max_bricks(P) / SCAN_SEG + 2)) + 256;
 }
 
 // mesh1 != nullptr: interlaced pair -- G is the shift-0 geometry, mesh1 gets the shift-0.5 twin
@@ -762,8 +767,10 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     unsigned int *counts = (unsigned int *)w; w += tab;
     unsigned int *brick_start = (unsigned int *)w; w += tab;
     unsigned int *cursor = (unsigned int *)w; w += tab;
+    unsigned int *filled = (unsigned int *)w; w += tab;
     unsigned int *seg_total = (unsigned int *)w; w += align256(4 * (max_bricks(P) / SCAN_SEG + 2));
-    unsigned int *counter = (unsigned int *)w;
+    unsigned int *seg_filled = (unsigned int *)w; w += align256(4 * (max_bricks(P) / SCAN_SEG + 2));
+    unsigned int *counter = (unsigned int *)w;          // [0] work queue, [1] number of non-empty bricks
 
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)P->num_sms * 8);
@@ -773,9 +780,9 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     APK_CUDA(cudaGetLastError());
     P->mark(1, st);
     const int nseg = (B.nbricks + SCAN_SEG - 1) / SCAN_SEG;
-    brick_segsum_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total);
+    brick_segsum_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total, seg_filled);
     APK_CUDA(cudaGetLastError());
-    brick_scan_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total, brick_start, cursor);
+    brick_scan_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total, seg_filled, brick_start, cursor, filled, counter + 1);
     APK_CUDA(cudaGetLastError());
     P->mark(2, st);
     brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT><<<pb, PART_THREADS, 0, st>>>(
@@ -791,11 +798,11 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     if (per_sm < 1) per_sm = 1;
     const int ctas = std::min(P->num_sms * per_sm, B.nbricks);
     P->mark(3, st);
-    kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, G, B, counter, mesh, PAIR ? 0 : -1);
+    kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G, B, counter, mesh, PAIR ? 0 : -1);
     APK_CUDA(cudaGetLastError());
     if (PAIR) {
         APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-        kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, G1, B, counter, mesh1, 1);
+        kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G1, B, counter, mesh1, 1);
         APK_CUDA(cudaGetLastError());
     }
     P->mark(4, st);

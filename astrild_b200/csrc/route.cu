@@ -114,11 +114,21 @@ route_group_kernel(const PT *__restrict__ stage_pos, const MT *__restrict__ stag
                    MT *__restrict__ out_mass) {
     const long long n = min((long long)*total, capacity);
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const PT x = stage_pos[3 * i];
-        int d = dest_rank<PT>(x, R);
-        if (d < 0) continue;                                         // cannot happen: staged particles leave
-        const unsigned long long slot = atomicAdd(cursor + d, 1ULL);
+    const long long n_pad = (n + 31) & ~31LL;                        // warp-uniform trip count
+    const int lane = threadIdx.x & 31;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+        PT x = 0;
+        int d = -1;
+        if (i < n) { x = stage_pos[3 * i]; d = dest_rank<PT>(x, R); }   // d < 0 cannot happen: staged particles leave
+        // one atomic per destination and warp: the leavers of a slab go to very few ranks (its two neighbours,
+        // as a rule), so per-particle atomics would all hit the same two addresses
+        const unsigned int peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long base = 0;
+        if (lane == leader && d >= 0) base = atomicAdd(cursor + d, (unsigned long long)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (d < 0) continue;
+        const unsigned long long slot = base + __popc(peers & ((1u << lane) - 1u));
         out_pos[3 * slot] = x; out_pos[3 * slot + 1] = stage_pos[3 * i + 1]; out_pos[3 * slot + 2] = stage_pos[3 * i + 2];
         if (stage_mass) out_mass[slot] = stage_mass[i];
     }

@@ -92,6 +92,12 @@ class CudaSlabBackend:
         _lib.call("apk_padded_mesh_sum", self.eng._plan, _ptr(owned), _ptr(out), self.eng.stream)
         return out
 
+    @staticmethod
+    def dc_sum(grid2d: torch.Tensor) -> torch.Tensor:
+        """Sum of the owned planes read off the (ky, kz) = (0, 0) column of their 2-D transforms (cuFFT is
+        un-normalised): n0 values instead of a pass over the mesh."""
+        return grid2d[:, 0, 0].real.sum(dtype=torch.float64).reshape(1)
+
     # -- 4./6. FFT stages ---------------------------------------------------------------------------
     def fft2d(self, owned: torch.Tensor) -> torch.Tensor:
         eng = self.eng
@@ -127,14 +133,24 @@ class CudaSlabBackend:
 
     def transpose_p2p(self, grids: list) -> list:
         buf, hdl = self._p2p
-        ny, Nk = self.N // self.nranks, self.N // 2 + 1
-        field_bytes = self.N * ny * Nk * 8
         hdl.barrier(channel=0)                    # every rank is done reading the previous step's buffers
         for f, g in enumerate(grids):
-            _lib.call("apk_slab_transpose_p2p", self.eng._plan, _ptr(g), ct.c_void_p(hdl.buffer_ptrs_dev),
-                      f * field_bytes, self.nranks, self.eng.stream)
+            self.transpose_p2p_store(f, g)
         hdl.barrier(channel=1)                    # every rank's blocks have landed
         return [buf[f] for f in range(len(grids))]
+
+    def transpose_p2p_store(self, f: int, g: torch.Tensor, stream=None) -> torch.Tensor:
+        """Pack + peer-store field f into every rank's receive buffer (no synchronisation: see p2p_barrier)."""
+        buf, hdl = self._p2p
+        ny, Nk = self.N // self.nranks, self.N // 2 + 1
+        st = self.eng.stream if stream is None else ct.c_void_p(stream.cuda_stream)
+        _lib.call("apk_slab_transpose_p2p", self.eng._plan, _ptr(g), ct.c_void_p(hdl.buffer_ptrs_dev),
+                  f * self.N * ny * Nk * 8, self.nranks, st)
+        return buf[f]
+
+    def p2p_barrier(self, channel: int) -> None:
+        """Device-side barrier of all ranks on the current stream (symmetric-memory signal pads)."""
+        self._p2p[1].barrier(channel=channel)
 
     # -- 7. binning ----------------------------------------------------------------------------------
     def make_binning(self, y0: int, ny: int, kmin, dk, kmax, compensation, interlaced):
@@ -278,51 +294,91 @@ class SlabPk:
         mark("start")
         # 1. route: only particles that change slab travel; the slab deposit ignores particles it
         #    does not own, so the caller's arrays are deposited as they are
-        parts = [(pos, mass)]
+        side = getattr(be, "side_stream", None)
+        overlap = side is not None and torch.cuda.is_available()
+        incoming = None                              # (positions, masses, event) of the particles other ranks send
         if not (routed or P == 1):
             sp, sm, counts = be.route(pos, mass, ps)
             mark("route")
-            fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
-            fm = self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows)) if sm is not None else None
-            if fp.shape[0]:
-                parts.append((fp, fm))
-            mark("exchange_particles")
+            if overlap:
+                # the all-to-all-v runs on the side stream while the own particles are deposited (issued below,
+                # BEFORE the host blocks on the exchanged counts)
+                main = torch.cuda.current_stream(be.device)
+                routed_ev = torch.cuda.Event()
+                routed_ev.record(main)
         # 2./3. deposit + ghosts
-        owned = []
-        if self.interlaced and hasattr(be, "deposit_pair"):
-            pair = None
-            for rp, rm in parts:
-                pair = be.deposit_pair(rp, rm, self.resampler, ps, out=pair)
-            mark("deposit")
-            owned = [self._exchange_ghosts(m) for m in pair]
-            mark("ghosts")
+        pair_mode = self.interlaced and hasattr(be, "deposit_pair")
+        shifts = (0.0, 0.5) if self.interlaced else (0.0,)
+        if pair_mode:
+            meshes = list(be.deposit_pair(pos, mass, self.resampler, ps))
         else:
-            for sh in ((0.0, 0.5) if self.interlaced else (0.0,)):
-                mesh = None
-                for rp, rm in parts:
-                    mesh = be.deposit(rp, rm, self.resampler, sh, ps, out=mesh)
-                mark("deposit")
-                owned.append(self._exchange_ghosts(mesh))
-                mark("ghosts")
-        total = be.mesh_sum(owned[0])
+            meshes = [be.deposit(pos, mass, self.resampler, sh, ps) for sh in shifts]
+        if not (routed or P == 1):
+            if overlap:
+                with torch.cuda.stream(side):
+                    side.wait_event(routed_ev)
+                    fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
+                    fm = (self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows))
+                          if sm is not None else None)
+                    arrived = torch.cuda.Event()
+                    arrived.record(side)
+                main.wait_event(arrived)
+                for t in (fp, fm, sp, sm):
+                    if t is not None:
+                        t.record_stream(main)
+                        t.record_stream(side)
+            else:
+                fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
+                fm = (self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows))
+                      if sm is not None else None)
+            if fp.shape[0]:
+                if pair_mode:
+                    meshes = list(be.deposit_pair(fp, fm, self.resampler, ps, out=tuple(meshes)))
+                else:
+                    meshes = [be.deposit(fp, fm, self.resampler, sh, ps, out=m) for sh, m in zip(shifts, meshes)]
+        mark("deposit")
+        owned = [self._exchange_ghosts(m) for m in meshes]
+        del meshes
+        mark("ghosts")
         # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
         #    pipelined per field: while field f is packed and exchanged on a side stream, the 2-D FFT of
         #    field f+1 (and later the 1-D FFT of field f-1) runs on the main stream
-        side = getattr(be, "side_stream", None)
         use_p2p = (P > 1 and self.p2p and isinstance(self.comm, TorchDistComm) and hasattr(be, "setup_p2p")
                    and be.setup_p2p(self.comm.group, 2 if self.interlaced else 1))
-        if use_p2p:
-            grids = [be.fft2d(o) for o in owned]
-            mark("fft2d")
-            grids = be.transpose_p2p(grids)
+        has_dc = hasattr(be, "dc_sum")
+        total = None
+        if use_p2p and side is not None:
+            # peer-store transposes on the side stream: field f travels over NVLink while the main stream
+            # transforms field f+1 (2-D) and, later, field f-1 (1-D)
+            main = torch.cuda.current_stream(be.device)
+            landed = []
+            for f, o in enumerate(owned):
+                g2 = be.fft2d(o)
+                if f == 0:
+                    total = be.dc_sum(g2) if has_dc else be.mesh_sum(o)
+                ready = torch.cuda.Event()
+                ready.record(main)
+                o.record_stream(side)                # the side stream reads these planes
+                with torch.cuda.stream(side):
+                    side.wait_event(ready)
+                    if f == 0:
+                        be.p2p_barrier(0)            # every rank is done reading the previous step's buffers
+                    be.transpose_p2p_store(f, g2, side)
+                    be.p2p_barrier(1 + (f & 1))      # field f has landed everywhere
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                landed.append(ev)
+            grids = []
+            for f, ev in enumerate(landed):
+                main.wait_event(ev)
+                grids.append(be.fft1d(be._p2p[0][f], self.ny))
             del owned
-            mark("transpose")
-            grids = [be.fft1d(g, self.ny) for g in grids]
-            mark("fft1d")
-        elif side is None or P == 1 or len(owned) == 1:
+            mark("fft+transpose")
+        elif use_p2p or side is None or P == 1 or len(owned) == 1:
             grids = [be.fft2d(o) for o in owned]
+            total = be.dc_sum(grids[0]) if has_dc else be.mesh_sum(owned[0])
             mark("fft2d")
-            grids = self._transpose(grids)
+            grids = be.transpose_p2p(grids) if use_p2p else self._transpose(grids)
             del owned
             mark("transpose")
             grids = [be.fft1d(g, self.ny) for g in grids]
@@ -330,8 +386,10 @@ class SlabPk:
         else:
             main = torch.cuda.current_stream(be.device)
             moved, done = [], []
-            for o in owned:
+            for f, o in enumerate(owned):
                 g2 = be.fft2d(o)
+                if f == 0:
+                    total = be.dc_sum(g2) if has_dc else be.mesh_sum(o)
                 ready = torch.cuda.Event()
                 ready.record(main)
                 o.record_stream(side)
