@@ -52,6 +52,8 @@ SIGNATURES = {
     "apk_fft_r2c_2d": [_vp, _vp, _vp],
     "apk_fft_c2c_1d": [_vp, _vp, _i, _vp],
     "apk_plan_prepare_fft1d": [_vp, _i],
+    "apk_plan_prepare_fft2d": [_vp],
+    "apk_plan_set_first_mesh_event": [_vp, _vp],
     "apk_binning_create": [ct.POINTER(_vp), _vp, _i, _i, _i] + [_vp] * 5 + [_i] + [_vp] * 6 + [_i, _i],
     "apk_binning_destroy": [_vp],
     "apk_bin_power": [_vp] * 9 + [_vp],

@@ -41,7 +41,8 @@ static int make_fft3d(apk_plan *P) {
     long long n[3] = {P->N, P->N, P->N};
     size_t ws = 0;
     APK_CUFFT(cufftMakePlanMany64(P->fft3d, 3, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, 1, &ws));
-    P->fft_work_bytes = ws > P->fft_work_bytes ? ws : P->fft_work_bytes;
+    P->fft_ws[0] = (ws + 255) & ~(size_t)255;
+    P->fft_work_bytes = P->fft_ws[0] + P->fft_ws[1] + P->fft_ws[2];
     P->has_fft3d = true;
     return 0;
 }
@@ -53,7 +54,8 @@ static int make_fft2d(apk_plan *P) {
     long long n[2] = {P->N, P->N};
     size_t ws = 0;
     APK_CUFFT(cufftMakePlanMany64(P->fft2d, 2, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, P->n0, &ws));
-    P->fft_work_bytes = ws > P->fft_work_bytes ? ws : P->fft_work_bytes;
+    P->fft_ws[1] = (ws + 255) & ~(size_t)255;
+    P->fft_work_bytes = P->fft_ws[0] + P->fft_ws[1] + P->fft_ws[2];
     P->has_fft2d = true;
     return 0;
 }
@@ -68,7 +70,8 @@ static int make_fft1d(apk_plan *P, int ny_local) {
     const long long stride = (long long)ny_local * P->Nk;
     size_t ws = 0;
     APK_CUFFT(cufftMakePlanMany64(P->fft1d, 1, n, embed, stride, 1, embed, stride, 1, CUFFT_C2C, stride, &ws));
-    P->fft_work_bytes = ws > P->fft_work_bytes ? ws : P->fft_work_bytes;
+    P->fft_ws[2] = (ws + 255) & ~(size_t)255;
+    P->fft_work_bytes = P->fft_ws[0] + P->fft_ws[1] + P->fft_ws[2];
     P->has_fft1d = true;
     P->fft1d_ny = ny_local;
     return 0;
@@ -141,8 +144,9 @@ int apk_plan_ghost_planes(const apk_plan *P, int *n_lo, int *n_hi) {
 int apk_plan_workspace_bytes(const apk_plan *P, int64_t max_particles, int with_mass, int interlaced, size_t *bytes) {
     APK_REQUIRE(P && bytes, "apk_plan_workspace_bytes: null argument");
     size_t dep = deposit_sorted_workspace_bytes(P, max_particles, with_mass, interlaced);
-    size_t fft = P->fft_work_bytes;
-    *bytes = (dep > fft ? dep : fft) + 256;
+    // the cuFFT work areas sit at the END of the workspace, one per plan, disjoint from the deposit's region at
+    // its start: a transform may run on another stream while a deposit is in flight
+    *bytes = ((dep + 255) & ~(size_t)255) + P->fft_work_bytes + 512;
     return 0;
 }
 
@@ -185,19 +189,19 @@ static int deposit_impl(apk_plan *P, const void *p0, const void *p1, const void 
     }
     if (method == APK_DEPOSIT_AUTO)
         method = (np >= (1 << 18)) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
-    P->dep_timed = false;
+    if (P->timing) P->dep_timed = false;            // an untimed call leaves the last timed deposit's events alone
     if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
         return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
     if (P->mark(3, st)) { set_error("apk_deposit: event record failed"); return 1; }
     int rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
     if (rc) return rc;
     if (mesh1) {
+        if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
         rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, geom(shift + 0.5), mesh1, P->num_sms, st);
         if (rc) return rc;
     }
     if (P->mark(4, st)) { set_error("apk_deposit: event record failed"); return 1; }
-    P->dep_timed = P->timing;
-    P->dep_sorted = false;
+    if (P->timing) { P->dep_timed = true; P->dep_sorted = false; }
     return 0;
 }
 
@@ -295,10 +299,17 @@ int apk_store_mesh(apk_plan *P, const float *mesh, double scale, double *value_m
 }
 
 static int check_work(apk_plan *P, const char *who) {
-    APK_REQUIRE(P->fft_work_bytes == 0 || (P->workspace && P->workspace_bytes >= P->fft_work_bytes),
+    APK_REQUIRE(P->fft_work_bytes == 0 || (P->workspace && P->workspace_bytes >= P->fft_work_bytes + 256),
                 "%s: workspace of %zu bytes needed, %zu set (apk_plan_set_workspace)", who,
-                P->fft_work_bytes, P->workspace_bytes);
+                P->fft_work_bytes + 256, P->workspace_bytes);
     return 0;
+}
+
+// work area of plan `which` (0: 3-D, 1: batched 2-D, 2: batched 1-D) at the tail of the workspace
+static void *fft_work_area(const apk_plan *P, int which) {
+    size_t off = (P->workspace_bytes - P->fft_work_bytes) & ~(size_t)255;
+    for (int i = 0; i < which; ++i) off += P->fft_ws[i];
+    return (char *)P->workspace + off;
 }
 
 int apk_fft_r2c(apk_plan *P, float *mesh, void *stream) {
@@ -308,7 +319,7 @@ int apk_fft_r2c(apk_plan *P, float *mesh, void *stream) {
     if (int rc = make_fft3d(P)) return rc;
     if (int rc = check_work(P, "apk_fft_r2c")) return rc;
     APK_CUFFT(cufftSetStream(P->fft3d, (cudaStream_t)stream));
-    if (P->fft_work_bytes) APK_CUFFT(cufftSetWorkArea(P->fft3d, P->workspace));
+    if (P->fft_ws[0]) APK_CUFFT(cufftSetWorkArea(P->fft3d, fft_work_area(P, 0)));
     APK_CUFFT(cufftExecR2C(P->fft3d, mesh, (cufftComplex *)mesh));
     return 0;
 }
@@ -319,7 +330,7 @@ int apk_fft_r2c_2d(apk_plan *P, float *mesh, void *stream) {
     if (int rc = make_fft2d(P)) return rc;
     if (int rc = check_work(P, "apk_fft_r2c_2d")) return rc;
     APK_CUFFT(cufftSetStream(P->fft2d, (cudaStream_t)stream));
-    if (P->fft_work_bytes) APK_CUFFT(cufftSetWorkArea(P->fft2d, P->workspace));
+    if (P->fft_ws[1]) APK_CUFFT(cufftSetWorkArea(P->fft2d, fft_work_area(P, 1)));
     APK_CUFFT(cufftExecR2C(P->fft2d, mesh, (cufftComplex *)mesh));
     return 0;
 }
@@ -330,13 +341,25 @@ int apk_plan_prepare_fft1d(apk_plan *P, int ny_local) {
     return make_fft1d(P, ny_local);
 }
 
+int apk_plan_prepare_fft2d(apk_plan *P) {
+    APK_REQUIRE(P, "apk_plan_prepare_fft2d: null plan");
+    DeviceGuard guard(P->device);
+    return make_fft2d(P);
+}
+
+int apk_plan_set_first_mesh_event(apk_plan *P, void *event) {
+    APK_REQUIRE(P, "apk_plan_set_first_mesh_event: null plan");
+    P->first_mesh_event = (cudaEvent_t)event;
+    return 0;
+}
+
 int apk_fft_c2c_1d(apk_plan *P, void *grid, int ny_local, void *stream) {
     APK_REQUIRE(P && grid && ny_local >= 1, "apk_fft_c2c_1d: bad argument");
     DeviceGuard guard(P->device);
     if (int rc = make_fft1d(P, ny_local)) return rc;
     if (int rc = check_work(P, "apk_fft_c2c_1d")) return rc;
     APK_CUFFT(cufftSetStream(P->fft1d, (cudaStream_t)stream));
-    if (P->fft_work_bytes) APK_CUFFT(cufftSetWorkArea(P->fft1d, P->workspace));
+    if (P->fft_ws[2]) APK_CUFFT(cufftSetWorkArea(P->fft1d, fft_work_area(P, 2)));
     APK_CUFFT(cufftExecC2C(P->fft1d, (cufftComplex *)grid, (cufftComplex *)grid, CUFFT_FORWARD));
     return 0;
 }

@@ -61,7 +61,9 @@ struct apk_plan {
     cufftHandle fft3d = 0;     bool has_fft3d = false;
     cufftHandle fft2d = 0;     bool has_fft2d = false;
     cufftHandle fft1d = 0;     bool has_fft1d = false;   int fft1d_ny = 0;
-    size_t fft_work_bytes = 0;
+    size_t fft_work_bytes = 0;  // sum of fft_ws
+    size_t fft_ws[3] = {0, 0, 0};   // cuFFT work areas (3-D, 2-D, 1-D plan), 256-byte multiples, at the tail of the workspace
+    cudaEvent_t first_mesh_event = nullptr;   // apk_plan_set_first_mesh_event
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
     double *scratch = nullptr;   // small device scratch for reductions (plan-owned)

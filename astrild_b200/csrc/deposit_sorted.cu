@@ -50,6 +50,9 @@ constexpr int DEP_THREADS = 256;                // 8 warps, each owns a 3 x 3 bl
 #ifndef APK_DEP_CTAS
 #define APK_DEP_CTAS 3
 #endif
+#ifndef APK_DEP_PERSISTENT
+#define APK_DEP_PERSISTENT 0      // 1: persistent CTAs pulling bricks from a queue (same speed; blocks stream overlap)
+#endif
 constexpr int DEP_CTAS_PER_SM = APK_DEP_CTAS;   // 3: 24 warps per SM at <= 85 registers
 constexpr int CH = 3072;                        // particles per shared-memory chunk
 static_assert(DEP_THREADS / 32 == (BX / 3) * (BY / 3), "one warp per 3 x 3 block of columns");
@@ -534,7 +537,9 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     float *sy = sx + CH;
     float *sz = sy + CH;
     float *sm = sz + CH;                                          // only if MASS
+#if APK_DEP_PERSISTENT
     __shared__ unsigned int s_info[3];
+#endif
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -546,11 +551,12 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     // this warp's 3 x 3 block of (x,y) columns inside the brick
     const int bi = warp / (BY / 3), bj = warp % (BY / 3);
 
+    const unsigned int nfilled = *nfilled_ptr;
+#if APK_DEP_PERSISTENT
     // Work queue over the list of non-empty bricks: thread 0 claims the NEXT entry while the current brick is
     // processed.  The dependent round trips (queue counter -> brick id -> the brick's particle range) are
     // spread over the sort phases so that no warp waits for them; the result is published in s_info before
     // the moments phase.
-    const unsigned int nfilled = *nfilled_ptr;
     if (tid == 0) {
         const unsigned int i0 = atomicAdd(work_counter, 1u);
         const unsigned int b0 = i0 < nfilled ? filled[i0] : (unsigned)B.nbricks;
@@ -565,6 +571,15 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
         if (brick >= (unsigned)B.nbricks) break;
         unsigned int ni = 0, nb = (unsigned)B.nbricks, nbeg = 0, nend = 0;
         if (tid == 0) ni = atomicAdd(work_counter, 1u);
+#else
+    // One CTA per non-empty brick, in list order (x-major: neighbouring windows meet in L2).  CTAs retire
+    // all the time, so kernels of a higher-priority stream (the slab path's FFT / transpose of the first mesh)
+    // get SMs while this one runs; a persistent grid would hold every register file until it ends.
+    for (unsigned int slot = blockIdx.x; slot < nfilled; slot += gridDim.x) {
+        if (slot != blockIdx.x) __syncthreads();
+        const unsigned int brick = filled[slot];
+        const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
+#endif
 
         const int bz = brick % B.nbz;
         const int by = (brick / B.nbz) % B.nby;
@@ -602,7 +617,9 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 }
             }
             __syncthreads();
+#if APK_DEP_PERSISTENT
             if (tid == 0 && c0 == pbeg && ni < nfilled) nb = filled[ni];
+#endif
 
             // ---- exclusive scan of the cell counts (9 per thread) ------------------------
             {
@@ -636,7 +653,9 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                 if (tid == DEP_THREADS - 1) cnt[BRICK_CELLS] = run;
             }
             __syncthreads();
+#if APK_DEP_PERSISTENT
             if (tid == 0 && c0 == pbeg && nb < (unsigned)B.nbricks) { nbeg = brick_start[nb]; nend = brick_start[nb + 1]; }
+#endif
 
             // ---- scatter into cell order --------------------------------------------------
 #pragma unroll
@@ -658,7 +677,9 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
                     }
                 }
             }
+#if APK_DEP_PERSISTENT
             if (tid == 0 && c0 == pbeg) { s_info[0] = nb; s_info[1] = nbeg; s_info[2] = nend; }
+#endif
             __syncthreads();
 
             // ---- moments per home cell; each warp walks its own 9 columns, no CTA barrier ----
@@ -796,18 +817,20 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     int per_sm = 1;
     APK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEP_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    const int ctas = std::min(P->num_sms * per_sm, B.nbricks);
+    // persistent: one wave; otherwise one CTA per brick (CTAs beyond the number of non-empty bricks, which only
+    // the device knows, exit at once)
+    const int ctas = APK_DEP_PERSISTENT ? std::min(P->num_sms * per_sm, B.nbricks) : B.nbricks;
     P->mark(3, st);
     kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G, B, counter, mesh, PAIR ? 0 : -1);
     APK_CUDA(cudaGetLastError());
     if (PAIR) {
+        if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
         APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
         kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G1, B, counter, mesh1, 1);
         APK_CUDA(cudaGetLastError());
     }
     P->mark(4, st);
-    P->dep_timed = P->timing;
-    P->dep_sorted = true;
+    if (P->timing) { P->dep_timed = true; P->dep_sorted = true; }
     return 0;
 }
 

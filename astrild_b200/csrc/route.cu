@@ -39,6 +39,8 @@ __device__ __forceinline__ int dest_rank(const PT x, const RouteGeom &R) {
     bool far = false;
     if constexpr (sizeof(PT) == 4) {
         const float pr = __fmul_rn(x, R.s0);
+        // well inside the slab (the rounded product is within ~1e-4 cells of the exact one): stays, no more work
+        if (pr > (float)R.x0 + 0.01f && pr < (float)(R.x0 + R.ppr) - 0.01f) return -1;
         float e = fmaf(x, R.s0, -pr);
         e = fmaf(x, R.s1, e);
         e = fmaf(x, R.s2, e);

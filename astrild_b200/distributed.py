@@ -43,45 +43,80 @@ class CudaSlabBackend:
         self.device = self.eng.device
         self.N, self.L, self.n0, self.nranks = N, L, n0, nranks
         self._counts = torch.zeros(2 * nranks, dtype=torch.int64, device=self.device)
-        self.side_stream = torch.cuda.Stream(self.device)     # transposes overlap the FFTs of the other field
+        # high priority: its kernels (exchange, first mesh's ghosts / FFT / transpose) take SMs as deposit CTAs retire
+        self.side_stream = torch.cuda.Stream(self.device, priority=-1)
 
     # -- 1. routing -----------------------------------------------------------------------
     def route(self, pos, mass, pos_scale: float):
         """Particles of this rank that belong to another slab, grouped by destination:
         (positions (n,3), masses or None, per-destination counts).  Everything else stays put."""
+        return self.route_end(self.route_begin(pos, mass, pos_scale))
+
+    def route_begin(self, pos, mass, pos_scale: float, capacity: int | None = None) -> dict:
+        """Launches the routing kernels on the current stream and returns without waiting for them."""
         eng = self.eng
         p0, p1, p2, layout, dt, npart, keep = eng._positions(pos)
         m = None
         if mass is not None:
             m = eng._to_device(mass).to(dt).contiguous()
         code = _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64
-        capacity = min(max(npart, 1), max(1 << 16, npart // 8))
-        while True:
-            eng.ensure_workspace(max(npart, capacity), m is not None)   # the leavers are staged in the plan workspace
-            out_pos = torch.empty((capacity, 3), dtype=dt, device=self.device)
-            out_mass = torch.empty(capacity, dtype=dt, device=self.device) if m is not None else None
-            _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),
-                      _ptr(m), code, int(npart), self.nranks, _ptr(self._counts), int(capacity), _ptr(out_pos),
-                      _ptr(out_mass), eng.stream)
-            counts = self._counts[: self.nranks].cpu().tolist()
-            total = int(sum(counts))
-            if total <= capacity:
-                break
-            capacity = total                      # rare: more than 1/8 of the particles change slab
-        del keep
-        return out_pos[:total], (None if out_mass is None else out_mass[:total]), counts
+        if capacity is None:
+            capacity = min(max(npart, 1), max(1 << 16, npart // 8))
+        eng.ensure_workspace(max(npart, capacity), m is not None)   # the leavers are staged in the plan workspace
+        out_pos = torch.empty((capacity, 3), dtype=dt, device=self.device)
+        out_mass = torch.empty(capacity, dtype=dt, device=self.device) if m is not None else None
+        _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),
+                  _ptr(m), code, int(npart), self.nranks, _ptr(self._counts), int(capacity), _ptr(out_pos),
+                  _ptr(out_mass), eng.stream)
+        return {"pos": pos, "mass": mass, "pos_scale": pos_scale, "capacity": capacity, "out_pos": out_pos,
+                "out_mass": out_mass, "keep": (keep, m)}
+
+    def route_end(self, h: dict):
+        """Reads the per-destination counts (blocks the host on the CURRENT stream, which must be ordered after
+        route_begin's) and returns (positions, masses, counts).  More leavers than the staging buffer holds (more
+        than 1/8 of the particles change slab: rare) means a second, larger pass after a device synchronise."""
+        counts = self._counts[: self.nranks].cpu().tolist()
+        total = int(sum(counts))
+        if total > h["capacity"]:
+            torch.cuda.synchronize(self.device)       # nothing else may be using the plan workspace
+            return self.route_end(self.route_begin(h["pos"], h["mass"], h["pos_scale"], capacity=total))
+        om = h["out_mass"]
+        return h["out_pos"][:total], (None if om is None else om[:total]), counts
 
     def empty_like_rows(self, like: torch.Tensor, rows: int) -> torch.Tensor:
         return torch.empty((rows,) + tuple(like.shape[1:]), dtype=like.dtype, device=self.device)
 
     # -- 2./3. deposit and ghost planes ---------------------------------------------------------
-    def deposit(self, pos_aos, mass, resampler: str, shift: float, pos_scale: float, out=None):
+    def deposit(self, pos_aos, mass, resampler: str, shift: float, pos_scale: float, out=None, method: str = "auto"):
         """Deposit into the slab buffer (with ghost planes); out != None accumulates into it."""
-        return self.eng.deposit(pos_aos, mass, resampler, shift, pos_scale, "auto", out=out, zero=out is None)
+        return self.eng.deposit(pos_aos, mass, resampler, shift, pos_scale, method, out=out, zero=out is None)
 
-    def deposit_pair(self, pos_aos, mass, resampler: str, pos_scale: float, out=None):
-        """Both interlaced twins (shift 0, 0.5) from one partition; out = (mesh, mesh_shifted) accumulates."""
-        return self.eng.deposit_pair(pos_aos, mass, resampler, pos_scale, "auto", out=out, zero=out is None)
+    def deposit_pair(self, pos_aos, mass, resampler: str, pos_scale: float, out=None, method: str = "auto",
+                     timed: bool = True):
+        """Both interlaced twins (shift 0, 0.5) from one partition; out = (mesh, mesh_shifted) accumulates.
+        timed=False keeps this call out of the plan's per-kernel timing (it runs beside another deposit)."""
+        was = self.eng.timing
+        if not timed and was:
+            self.eng.enable_timing(False)
+        try:
+            return self.eng.deposit_pair(pos_aos, mass, resampler, pos_scale, method, out=out, zero=out is None)
+        finally:
+            if not timed and was:
+                self.eng.enable_timing(True)
+
+    def prepare_ffts(self, ny: int) -> None:
+        """Create both slab FFT plans now, so that the next workspace request already includes their work areas."""
+        _lib.call("apk_plan_prepare_fft2d", self.eng._plan)
+        _lib.call("apk_plan_prepare_fft1d", self.eng._plan, int(ny))
+
+    def set_first_mesh_event(self, event) -> None:
+        """event: a recorded torch.cuda.Event or None; see apk_plan_set_first_mesh_event."""
+        _lib.call("apk_plan_set_first_mesh_event", self.eng._plan,
+                  ct.c_void_p(event.cuda_event) if event is not None else None)
+
+    def zeroed_meshes(self, count: int) -> list:
+        """Slab buffers (with ghost planes), zeroed on the current stream."""
+        return [self.eng.new_mesh(ghosts=True).zero_() for _ in range(count)]
 
     def accumulate(self, dst: torch.Tensor, src: torch.Tensor) -> None:
         assert dst.is_contiguous() and src.is_contiguous() and dst.numel() == src.numel()
@@ -222,6 +257,13 @@ class SlabPk:
 
     def __init__(self, Nmesh: int, BoxSize: float, resampler: str = "tsc", interlaced: bool = False,
                  compensated: bool = False, device=None, group=None, backend=None, comm=None):
+        if comm is None and group is None and dist.is_initialized() and dist.get_world_size() > 1 \
+                and dist.get_backend() == "nccl" and os.environ.get("APK_SLAB_HP_NCCL", "1") != "0":
+            # NCCL's kernels run on its own internal stream.  At default priority they would queue behind the
+            # deposit's grid, and so would everything the side stream does after them: a communicator with
+            # high-priority streams lets the exchanges run WHILE the deposit kernels do.
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            group = dist.new_group(ranks=list(range(dist.get_world_size())), backend="nccl", pg_options=opts)
         self.comm = comm if comm is not None else TorchDistComm(group)
         self.P, self.rank = self.comm.P, self.comm.rank
         self.N, self.L = int(Nmesh), float(BoxSize)
@@ -249,16 +291,24 @@ class SlabPk:
         b = ((self.rank + 1) * n) // self.P
         return a, b
 
-    def _exchange_ghosts(self, mesh: torch.Tensor) -> torch.Tensor:
-        """Send ghost planes to the ring neighbours, add what arrives; returns the owned planes."""
+    def _exchange_ghosts(self, meshes: list) -> list:
+        """Send the ghost planes of every mesh to the ring neighbours (one batch of sends and receives for all
+        of them), add what arrives; returns the owned planes."""
         lo, hi, n0 = self.ghost_lo, self.ghost_hi, self.n0
         if self.P == 1:
-            return mesh                                  # whole periodic mesh: the kernel wrapped already
-        owned = mesh[lo: lo + n0]
+            return list(meshes)                          # whole periodic mesh: the kernel wrapped already
         # ghost_lo is the previous rank's last plane, ghost_hi the next rank's first planes
-        from_next, from_prev = self.comm.ring_exchange(mesh[:lo].contiguous(), mesh[lo + n0:].contiguous())
-        self.backend.accumulate(owned[n0 - lo:], from_next)
-        self.backend.accumulate(owned[:hi], from_prev)
+        to_prev = torch.stack([m[:lo] for m in meshes]) if len(meshes) > 1 else meshes[0][:lo].contiguous()
+        to_next = torch.stack([m[lo + n0:] for m in meshes]) if len(meshes) > 1 else meshes[0][lo + n0:].contiguous()
+        from_next, from_prev = self.comm.ring_exchange(to_prev, to_next)
+        if len(meshes) == 1:
+            from_next, from_prev = from_next[None], from_prev[None]
+        owned = []
+        for f, m in enumerate(meshes):
+            o = m[lo: lo + n0]
+            self.backend.accumulate(o[n0 - lo:], from_next[f])
+            self.backend.accumulate(o[:hi], from_prev[f])
+            owned.append(o)
         return owned
 
     def _transpose(self, grids: list) -> list:
@@ -292,6 +342,12 @@ class SlabPk:
                 marks.append((name, ev))
 
         mark("start")
+        side = getattr(be, "side_stream", None)
+        if (P > 1 and self.interlaced and self.p2p and side is not None and torch.cuda.is_available()
+                and isinstance(self.comm, TorchDistComm) and hasattr(be, "setup_p2p")
+                and be.setup_p2p(self.comm.group, 2)):
+            grids, total = self._pipelined_pair(pos, mass, ps, routed, mark)
+            return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark)
         # 1. route: only particles that change slab travel; the slab deposit ignores particles it
         #    does not own, so the caller's arrays are deposited as they are
         side = getattr(be, "side_stream", None)
@@ -309,35 +365,50 @@ class SlabPk:
         # 2./3. deposit + ghosts
         pair_mode = self.interlaced and hasattr(be, "deposit_pair")
         shifts = (0.0, 0.5) if self.interlaced else (0.0,)
-        if pair_mode:
-            meshes = list(be.deposit_pair(pos, mass, self.resampler, ps))
-        else:
-            meshes = [be.deposit(pos, mass, self.resampler, sh, ps) for sh in shifts]
-        if not (routed or P == 1):
-            if overlap:
-                with torch.cuda.stream(side):
-                    side.wait_event(routed_ev)
-                    fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
-                    fm = (self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows))
-                          if sm is not None else None)
-                    arrived = torch.cuda.Event()
-                    arrived.record(side)
-                main.wait_event(arrived)
-                for t in (fp, fm, sp, sm):
-                    if t is not None:
-                        t.record_stream(main)
-                        t.record_stream(side)
-            else:
+
+        def deposit_into(rp, rm, meshes, method="auto"):
+            if pair_mode:
+                return list(be.deposit_pair(rp, rm, self.resampler, ps, out=None if meshes is None else tuple(meshes),
+                                            **({} if method == "auto" else {"method": method})))
+            return [be.deposit(rp, rm, self.resampler, sh, ps, out=None if meshes is None else meshes[i],
+                               **({} if method == "auto" else {"method": method})) for i, sh in enumerate(shifts)]
+
+        if routed or P == 1:
+            meshes = deposit_into(pos, mass, None)
+        elif overlap and hasattr(be, "zeroed_meshes"):
+            # own particles on the main stream; meanwhile, on the side stream, the leavers are exchanged and --
+            # a small set near the slab faces -- added with plain REDs into the same meshes
+            meshes = be.zeroed_meshes(len(shifts))
+            zeroed = torch.cuda.Event()
+            zeroed.record(main)
+            deposit_into(pos, mass, meshes)
+            with torch.cuda.stream(side):
+                side.wait_event(routed_ev)
                 fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
                 fm = (self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows))
                       if sm is not None else None)
+                small = fp.shape[0] < (1 << 22)
+                if small and fp.shape[0]:
+                    side.wait_event(zeroed)
+                    deposit_into(fp, fm, meshes, method="atomic")
+                arrived = torch.cuda.Event()
+                arrived.record(side)
+            main.wait_event(arrived)
+            for t in (fp, fm, sp, sm):
+                if t is not None:
+                    t.record_stream(main)
+                    t.record_stream(side)
+            if not small:
+                deposit_into(fp, fm, meshes)
+        else:
+            meshes = deposit_into(pos, mass, None)
+            fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
+            fm = (self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows))
+                  if sm is not None else None)
             if fp.shape[0]:
-                if pair_mode:
-                    meshes = list(be.deposit_pair(fp, fm, self.resampler, ps, out=tuple(meshes)))
-                else:
-                    meshes = [be.deposit(fp, fm, self.resampler, sh, ps, out=m) for sh, m in zip(shifts, meshes)]
+                deposit_into(fp, fm, meshes)
         mark("deposit")
-        owned = [self._exchange_ghosts(m) for m in meshes]
+        owned = self._exchange_ghosts(meshes)
         del meshes
         mark("ghosts")
         # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
@@ -407,6 +478,83 @@ class SlabPk:
                 grids.append(be.fft1d(t, self.ny))
             del owned
             mark("fft+transpose")
+        return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark)
+
+    def _pipelined_pair(self, pos, mass, ps: float, routed: bool, mark):
+        """Interlaced twins on P > 1 GPUs with peer-mapped transposes: everything that concerns mesh 0 after its
+        tile kernel -- ghost planes, 2-D FFT, peer-store transpose -- runs on the side stream WHILE the main
+        stream still deposits mesh 1 (an issue-bound kernel; the side work is bandwidth- and NVLink-bound), and
+        so do the particle exchange and the (few) received particles, which are added with plain REDs.
+        Returns (transposed k-grids [N][ny][Nk] of both meshes, total mass tensor)."""
+        be = self.backend
+        main, side = torch.cuda.current_stream(be.device), be.side_stream
+        be.prepare_ffts(self.ny)                     # plans first: they size the workspace once
+        sp = sm = fp = fm = None
+        if not routed:
+            pending = be.route_begin(pos, mass, ps)  # the counts are read later, on the side stream: no idle GPU
+        meshes = be.zeroed_meshes(2)
+        for m in meshes:
+            m.record_stream(side)
+        begun = torch.cuda.Event()
+        begun.record(main)                           # meshes zeroed, leavers staged
+        first = torch.cuda.Event()
+        first.record(main)                           # (creates the handle; re-recorded inside the library)
+        be.set_first_mesh_event(first)
+        try:
+            be.deposit_pair(pos, mass, self.resampler, ps, out=tuple(meshes))
+        finally:
+            be.set_first_mesh_event(None)
+        both = torch.cuda.Event()
+        both.record(main)
+        mesh0_ready = first
+        if not routed:
+            with torch.cuda.stream(side):
+                side.wait_event(begun)
+                sp, sm, counts = be.route_end(pending)
+                fp = self.comm.all_to_all_rows(sp, counts, lambda rows: be.empty_like_rows(sp, rows))
+                fm = (self.comm.all_to_all_rows(sm, counts, lambda rows: be.empty_like_rows(sm, rows))
+                      if sm is not None else None)
+                small = fp.shape[0] < (1 << 22)
+                if small and fp.shape[0]:
+                    be.deposit_pair(fp, fm, self.resampler, ps, out=tuple(meshes), method="atomic", timed=False)
+                arrived = torch.cuda.Event()
+                arrived.record(side)
+            for t in (fp, fm, sp, sm):
+                if t is not None:
+                    t.record_stream(main)
+                    t.record_stream(side)
+            if not small:                            # many leavers: sorted deposit after the own particles
+                main.wait_event(arrived)
+                be.deposit_pair(fp, fm, self.resampler, ps, out=tuple(meshes))
+                both = torch.cuda.Event()
+                both.record(main)
+                mesh0_ready = both
+        mark("deposit")
+        landed = []
+        with torch.cuda.stream(side):
+            for f in range(2):
+                side.wait_event(mesh0_ready if f == 0 else both)
+                owned = self._exchange_ghosts([meshes[f]])[0]
+                g2 = be.fft2d(owned)
+                if f == 0:
+                    total = be.dc_sum(g2)
+                    total.record_stream(main)
+                    be.p2p_barrier(0)                # every rank is done reading the previous step's buffers
+                be.transpose_p2p_store(f, g2, side)
+                be.p2p_barrier(1 + f)                # field f has landed everywhere
+                ev = torch.cuda.Event()
+                ev.record(side)
+                landed.append(ev)
+        grids = []
+        for f, ev in enumerate(landed):
+            main.wait_event(ev)
+            grids.append(be.fft1d(be._p2p[0][f], self.ny))
+        del meshes
+        mark("ghosts+fft+transpose")
+        return grids, total
+
+    def _finish(self, grids, total, kmin, dk, kmax, normalize, marks, mark) -> dict:
+        be, P = self.backend, self.P
         # 7. binning on the transposed slab
         comp = (self.resampler, self.interlaced) if self.compensated else None
         binning = be.make_binning(self.y0, self.ny, kmin, dk, kmax, comp, self.interlaced)

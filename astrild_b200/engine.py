@@ -110,13 +110,18 @@ class PkEngine:
         _lib.call("apk_plan_workspace_bytes", self._plan, int(max_particles), int(with_mass), int(interlaced),
                   ct.byref(need))
         if self._workspace is None or self._workspace.numel() < need.value:
+            if self._workspace is not None:
+                torch.cuda.synchronize(self.device)      # another stream may still be working in the old one
             self._workspace = None
             self._workspace = torch.empty(need.value, dtype=torch.uint8, device=self.device)
             _lib.call("apk_plan_set_workspace", self._plan, _ptr(self._workspace), self._workspace.numel())
 
     # ------------------------------------------------------------------ per-kernel timing
+    timing = False
+
     def enable_timing(self, on: bool = True) -> None:
         _lib.call("apk_plan_enable_timing", self._plan, int(on))
+        self.timing = bool(on)
 
     def last_deposit_ms(self) -> dict:
         ms = (ct.c_float * 4)()

@@ -58,7 +58,7 @@ int apk_plan_mesh_elems(const apk_plan *plan, int64_t *elems);
 /* bytes of scratch apk_deposit (sorted path, max_particles; interlaced != 0: apk_deposit_interlaced)
  * and apk_fft_r2c need                                                                         */
 int apk_plan_workspace_bytes(const apk_plan *plan, int64_t max_particles, int with_mass, int interlaced,
-                             size_t *bytes);
+                             size_t *bytes);   /* deposit region + the cuFFT work areas of the plans made so far */
 int apk_plan_set_workspace(apk_plan *plan, void *workspace, size_t bytes);
 /* slab plans deposit into n_lo + n0 + n_hi planes (ghosts below/above the owned slab, to be
  * sent to and added by the ring neighbours); single-GPU plans report 0, 0.                    */
@@ -95,6 +95,12 @@ int apk_deposit_interlaced(apk_plan *plan, const void *p0, const void *p1, const
                            int pos_dtype, double pos_scale, const void *mass, int mass_dtype, int64_t np,
                            int resampler, int method, int zero_first, float *mesh, float *mesh_shifted,
                            void *stream);
+
+/* `event` is a cudaEvent_t (NULL clears it).  While set, apk_deposit_interlaced records it on its stream as soon
+ * as the first mesh (shift 0) is complete, so that the caller can start that mesh's ghost exchange and FFT on
+ * another stream while the twin is still being deposited.  The cuFFT work areas live at the end of the
+ * workspace, disjoint from the deposit's region, for that reason.                                          */
+int apk_plan_set_first_mesh_event(apk_plan *plan, void *event);
 
 /* ---- slab routing (multi-GPU) ---------------------------------------------------------------- */
 /* Extracts the particles that must LEAVE this rank: destination = owner of the x-slab holding
@@ -144,6 +150,7 @@ int apk_fft_r2c(apk_plan *plan, float *mesh, void *stream);
 int apk_fft_r2c_2d(apk_plan *plan, float *mesh, void *stream);
 /* creates the 1-D plan for ny_local ahead of time so apk_plan_workspace_bytes accounts for it  */
 int apk_plan_prepare_fft1d(apk_plan *plan, int ny_local);
+int apk_plan_prepare_fft2d(apk_plan *plan);
 int apk_fft_c2c_1d(apk_plan *plan, void *grid, int ny_local, void *stream);
 
 /* ---- binning (FFTPower mode="1d") ---------------------------------------------------------- */
