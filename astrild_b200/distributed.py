@@ -342,6 +342,11 @@ class SlabPk:
                 marks.append((name, ev))
 
         mark("start")
+        eng = getattr(be, "eng", None)
+        if eng is not None:                          # host inputs: ONE upload serves routing and deposit
+            pos = tuple(eng._to_device(c) for c in pos) if isinstance(pos, (tuple, list)) else eng._to_device(pos)
+            if mass is not None and not np.isscalar(mass):
+                mass = eng._to_device(mass)
         side = getattr(be, "side_stream", None)
         if (P > 1 and self.interlaced and self.p2p and side is not None and torch.cuda.is_available()
                 and isinstance(self.comm, TorchDistComm) and hasattr(be, "setup_p2p")

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -326,22 +327,29 @@ def run_ours(args, wl_key: str) -> None:
     t_end.record()
     barrier()
     ms = t_start.elapsed_time(t_end)
-    dep_ms_rank0 = eng.last_deposit_ms() if world > 1 else None     # own-particle deposit of the last timed step
-    # one nvidia-smi query takes 0.2-0.4 s: a few samples need ~1.5 s of load: if the timed region was shorter, the same step keeps
-    # running (untimed) under the sampler
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    dep_ms_rank0 = None
+    if world > 1:
+        try:
+            dep_ms_rank0 = eng.last_deposit_ms()                    # own-particle deposit of the last timed step
+        except Exception:
+            dep_ms_rank0 = None
+    # one nvidia-smi query takes 0.2-0.4 s: a few samples need ~1.5 s of load.  If the timed region was shorter,
+    # the same step keeps running (untimed) under the sampler.  The count comes from the all-reduced time, so
+    # every rank runs the same number of (collective) steps.
     extra_steps = 0
-    while ms + extra_steps * (ms / args.steps) < 1500.0 and extra_steps < 400:
+    if ms < 1500.0:
+        extra_steps = min(400, int(math.ceil((1500.0 - ms) / max(ms / args.steps, 1e-3))))
+    for _ in range(extra_steps):
         step()
-        extra_steps += 1
     barrier()
     clocks = sampler.stop()
     if clocks is not None:
         clocks["untimed_steps_under_sampler"] = extra_steps
     slab_profile = dict(runner.last_profile) if world > 1 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
     ms_per_step = ms / args.steps
     value = Np / (ms_per_step * 1e-3) / 1e6
 
