@@ -65,7 +65,7 @@ def cpu_step(wl: dict, threads: int, sample_particles: int, sample_planes: int, 
     passes = 2 if wl["interlaced"] else 1
     t0 = time.perf_counter()
     for i in range(passes):
-        f.paint(state["pos"], None, N, L, wl["resampler"], 0.5 * i, out=state["canvas"])
+        f.paint(state["pos"], None, N, L, wl["resampler"], 0.5 * i, out=state["canvas"], threads=threads)
     t_dep = (time.perf_counter() - t0) * (Np / ns)
     # FFT sample: the 3-D r2c is N planes of 2-D r2c over (y,z) + N*Nk pencils of 1-D c2c along x.
     sp = min(sample_planes, N)
@@ -126,7 +126,7 @@ def lattice_sample(wl: dict, ns: int) -> np.ndarray:
 
 def cpu_sample_desc(wl, sample_particles, sample_planes, threads):
     return (f"deposit of the first {min(sample_particles, wl['n'] ** 3)} particles (lattice order) onto the full {wl['mesh']}^3 f64 mesh "
-            f"(1 thread, scaled to Np); {min(sample_planes, wl['mesh'])} of {wl['mesh']} planes of 2-D r2c + as many "
+            f"({threads} thread{'s, x-planes dealt round-robin' if threads > 1 else ''}, scaled to Np); {min(sample_planes, wl['mesh'])} of {wl['mesh']} planes of 2-D r2c + as many "
             f"x-pencil blocks of 1-D c2c (scipy pocketfft f64, {threads} threads, scaled); binning of "
             f"{min(sample_planes, wl['mesh'])} x-planes ({threads} threads, scaled)")
 
@@ -141,7 +141,7 @@ def run_reference(args, wl_key: str) -> None:
     f.build()
     wl = WORKLOADS[wl_key]
     threads = os.cpu_count() or 1
-    sp, spl = 1 << 22, 32
+    sp, spl = (1 << 24 if threads >= 4 else 1 << 22), 32
     state: dict = {}
     for _ in range(args.warmup):
         cpu_step(wl, threads, sp, spl, state)

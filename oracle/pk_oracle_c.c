@@ -67,6 +67,58 @@ void orc_paint(const void *p0, const void *p1, const void *p2, int layout, int i
     }
 }
 
+/* The same deposit for one of `nthreads` workers (pmesh's paint is single-threaded; this exists so that the CPU arm
+ * of the benchmark can use all host cores).  The y axis is cut into 2*nthreads blocks of `by` rows (the last one takes
+ * the remainder); in phase 0 worker `tid` deposits the particles whose HOME row lies in block 2*tid, in phase 1 those
+ * of block 2*tid+1.  Blocks handled at the same time are a whole block apart (by >= support), so their windows never
+ * meet, also across the periodic wrap (first block: phase 0, last block: phase 1); the caller runs phase 0 on all
+ * workers, waits, then phase 1.  Deterministic for a given thread count; differs from orc_paint only in the order of
+ * the float64 additions of cells next to a block boundary. */
+void orc_paint_yblocks(const void *p0, const void *p1, const void *p2, int layout, int is_f32,
+                       const void *mass, int mass_is_f32, int64_t Np, int N, double L, int support,
+                       double shift, double *canvas, int tid, int nthreads, int phase) {
+    const double scale = (double)N / L;
+    const int nblocks = 2 * nthreads;
+    const int by = N / nblocks;
+    const int mine = 2 * tid + phase;
+    for (int64_t p = 0; p < Np; ++p) {
+        const void *basey = layout ? p1 : p0;
+        int64_t iy = layout ? p : 3 * p + 1;
+        double yy = is_f32 ? (double)((const float *)basey)[iy] : ((const double *)basey)[iy];
+        /* home row = window base + left = floor(g + (support odd ? 0.5 : 0)), see window_1d: the scan over
+         * the particles of other workers costs one floor each */
+        int64_t hy = (int64_t)floor(yy * scale + shift + ((support & 1) ? 0.5 : 0.0));
+        int blk = (int)(wrap(hy, N) / by);
+        if (blk >= nblocks) blk = nblocks - 1;
+        if (blk != mine) continue;
+        int64_t i0y;
+        double wy[3];
+        window_1d(support, yy * scale + shift, &i0y, wy);
+        double x[3];
+        for (int d = 0; d < 3; d += 2) {
+            const void *base = layout ? (d == 0 ? p0 : p2) : p0;
+            int64_t idx = layout ? p : 3 * p + d;
+            x[d] = is_f32 ? (double)((const float *)base)[idx] : ((const double *)base)[idx];
+        }
+        double m = 1.0;
+        if (mass) m = mass_is_f32 ? (double)((const float *)mass)[p] : ((const double *)mass)[p];
+        int64_t i0[3];
+        double w[3][3];
+        i0[1] = i0y;
+        for (int j = 0; j < support; ++j) w[1][j] = wy[j];
+        for (int d = 0; d < 3; d += 2) window_1d(support, x[d] * scale + shift, &i0[d], w[d]);
+        for (int jx = 0; jx < support; ++jx) {
+            int64_t cx = wrap(i0[0] + jx, N) * (int64_t)N * N;
+            for (int jy = 0; jy < support; ++jy) {
+                int64_t cxy = cx + wrap(i0[1] + jy, N) * (int64_t)N;
+                double wxy = m * w[0][jx] * w[1][jy];
+                for (int jz = 0; jz < support; ++jz)
+                    canvas[cxy + wrap(i0[2] + jz, N)] += wxy * w[2][jz];
+            }
+        }
+    }
+}
+
 /* numpy.digitize(x, bins) for increasing bins == searchsorted(bins, x, side='right') */
 static inline int digitize(double x, const double *bins, int n) {
     int lo = 0, hi = n;

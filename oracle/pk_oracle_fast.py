@@ -37,6 +37,8 @@ def lib():
         _lib.orc_paint.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_int,
                                    ct.c_void_p, ct.c_int, ct.c_int64, ct.c_int, ct.c_double,
                                    ct.c_int, ct.c_double, ct.c_void_p]
+        _lib.orc_paint_yblocks.restype = None
+        _lib.orc_paint_yblocks.argtypes = _lib.orc_paint.argtypes + [ct.c_int, ct.c_int, ct.c_int]
         _lib.orc_bin_power.restype = None
         _lib.orc_bin_power.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int] + [ct.c_void_p] * 4 + [
             ct.c_int, ct.c_double] + [ct.c_void_p] * 4 + [ct.c_int, ct.c_int]
@@ -48,8 +50,10 @@ def _ptr(a):
 
 
 def paint(pos, mass, N: int, L: float, resampler: str = "cic", shift: float = 0.0,
-          out: np.ndarray | None = None) -> np.ndarray:
-    """Scalar-loop twin of pk_oracle.paint.  pos: (Np,3) AoS or tuple (x,y,z) SoA; f32 or f64."""
+          out: np.ndarray | None = None, threads: int = 1) -> np.ndarray:
+    """Scalar-loop twin of pk_oracle.paint.  pos: (Np,3) AoS or tuple (x,y,z) SoA; f32 or f64.
+    threads > 1: workers own blocks of y-rows, two phases (orc_paint_yblocks); deterministic, equal to the
+    single-threaded canvas up to the order of float64 additions next to block boundaries."""
     support = _o.RESAMPLER_SUPPORT[resampler]
     if isinstance(pos, (tuple, list)):
         x, y, z = (np.ascontiguousarray(a) for a in pos)
@@ -68,9 +72,16 @@ def paint(pos, mass, N: int, L: float, resampler: str = "cic", shift: float = 0.
         if m.dtype not in (np.float32, np.float64):
             m = m.astype(np.float64)
     canvas = np.zeros((N, N, N), dtype=np.float64) if out is None else out
-    lib().orc_paint(ptrs[0], ptrs[1], ptrs[2], layout, int(is32), _ptr(m),
-                    int(m is not None and m.dtype == np.float32), Np, N, float(L), support,
-                    float(shift), _ptr(canvas))
+    args = (ptrs[0], ptrs[1], ptrs[2], layout, int(is32), _ptr(m),
+            int(m is not None and m.dtype == np.float32), Np, N, float(L), support, float(shift), _ptr(canvas))
+    threads = max(1, min(int(threads), N // (2 * max(support, 2))))     # blocks of at least `support` rows
+    if threads == 1:
+        lib().orc_paint(*args)
+    else:
+        fn = lib().orc_paint_yblocks
+        with ThreadPoolExecutor(threads) as ex:
+            for phase in (0, 1):
+                list(ex.map(lambda t: fn(*args, t, threads, phase), range(threads)))
     if mass is not None and np.isscalar(mass) and mass != 1.0:
         canvas *= mass
     del keep
@@ -135,7 +146,7 @@ def power_from_particles(pos, mass, N: int, L: float, resampler: str = "tsc",
     def field(p, m):
         dx = L / N
         t0 = time.perf_counter()
-        real = paint(p, m, N, L, resampler)
+        real = paint(p, m, N, L, resampler, threads=threads)
         t["deposit"] += time.perf_counter() - t0
         scale = (N ** 3 / real.sum()) if normalize else 1.0 / dx ** 3
         t0 = time.perf_counter()
@@ -144,7 +155,7 @@ def power_from_particles(pos, mass, N: int, L: float, resampler: str = "tsc",
         c *= scale
         if interlaced:
             t0 = time.perf_counter()
-            real2 = paint(p, m, N, L, resampler, shift=0.5)
+            real2 = paint(p, m, N, L, resampler, shift=0.5, threads=threads)
             t["deposit"] += time.perf_counter() - t0
             t0 = time.perf_counter()
             c2_ = _o.r2c(real2, workers)
