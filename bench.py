@@ -16,9 +16,11 @@ Inputs are far larger than L2 (126 MB), so no explicit L2 flush is needed betwee
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import math
 import os
+import signal
 import statistics
 import subprocess
 import sys
@@ -226,7 +228,8 @@ def run_ours(args, wl_key: str) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # a stuck collective aborts after 3 minutes instead of holding the box (NCCL watchdog)
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     import astrild_b200 as ab
     from astrild_b200 import synthetic
@@ -498,6 +501,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (diagnostic runs only)")
     args = ap.parse_args()
+    # whole-run watchdog: a dead-lock (collectives, device-side barriers) must not hold the GPUs for long
+    limit = int(os.environ.get("APK_BENCH_TIME_LIMIT_S", "1500"))
+    if limit > 0 and hasattr(signal, "SIGALRM"):
+        def _expired(signum, frame):
+            sys.stderr.write(f"bench.py: no result after {limit} s -- giving up (rank {os.environ.get('RANK', '0')})\n")
+            sys.stderr.flush()
+            os._exit(124)
+        signal.signal(signal.SIGALRM, _expired)
+        signal.alarm(limit)
     wl = pick_workload(args)
     if args.impl == "reference":
         run_reference(args, wl)
