@@ -1,0 +1,126 @@
+"""The deposit kernels' SOURCE, executed on the CPU by tests/simt (fibers instead of GPU threads), against the oracle.
+
+No GPU needed: this checks the kernels' logic -- brick keys, the shared partition of the interlaced twins, the
+in-brick counting sort, moments, warp shuffles, window flush, slab ownership -- with a scheduler that resumes the
+threads of a CTA in pseudo-random order, so a missing barrier gives a wrong mesh.  The product never runs this way
+(tests/simt is test infrastructure; the CUDA library has no CPU path).  The GPU parity tests proper are
+tests/test_gpu_parity.py.
+"""
+import ctypes as ct
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "simt"))
+
+
+def load(path):
+    lib = ct.CDLL(path)
+    lib.simt_deposit_sorted.restype = ct.c_longlong
+    lib.simt_deposit_sorted.argtypes = ([ct.c_void_p] * 3 + [ct.c_int, ct.c_int, ct.c_void_p, ct.c_int, ct.c_longlong, ct.c_int,
+                                        ct.c_double, ct.c_double, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p, ct.c_void_p, ct.c_int])
+    return lib
+
+
+@pytest.fixture(scope="module")
+def simt():
+    import build_simt
+    return load(build_simt.build())
+
+
+def deposit(lib, pos, mass, N, L, resampler, pair=False, shift=0.0, soa=False, x0=0, n0=None):
+    """-> (mesh, twin or None) as float64 [planes][N][N]; planes = N, or 1 + n0 + 2 for a slab [x0, x0 + n0)."""
+    n0 = N if n0 is None else n0
+    planes = N if n0 == N else n0 + 3
+    m0 = np.zeros((planes, N, 2 * (N // 2 + 1)), np.float32)
+    m1 = np.zeros_like(m0) if pair else None
+    if soa:
+        cols = [np.ascontiguousarray(pos[:, d]) for d in range(3)]
+        ptrs, f64 = [c.ctypes.data for c in cols], cols[0].dtype == np.float64
+    else:
+        p = np.ascontiguousarray(pos)
+        ptrs, f64 = [p.ctypes.data, None, None], p.dtype == np.float64
+    mp = None if mass is None else np.ascontiguousarray(mass)
+    lib.simt_deposit_sorted(ptrs[0], ptrs[1], ptrs[2], int(soa), int(f64), None if mp is None else mp.ctypes.data,
+                            int(mp is not None and mp.dtype == np.float64), len(pos), N, 1.0 / L, shift,
+                            {"cic": 2, "tsc": 3}[resampler], x0, n0, m0.ctypes.data,
+                            None if m1 is None else m1.ctypes.data, 2)
+    return m0[:, :, :N].astype(np.float64), (None if m1 is None else m1[:, :, :N].astype(np.float64))
+
+
+def close(got, want):
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-6 * max(want.max(), 1.0))
+
+
+@pytest.mark.parametrize("resampler", ["cic", "tsc"])
+def test_interlaced_pair_on_cpu_fibers(simt, oracle_fast, resampler):
+    rng = np.random.default_rng(3)
+    N, L = 32, 1000.0
+    pos = (rng.random((12000, 3)) * L).astype(np.float32)
+    a, b = deposit(simt, pos, None, N, L, resampler, pair=True)
+    close(a, oracle_fast.paint(pos, None, N, L, resampler, 0.0))
+    close(b, oracle_fast.paint(pos, None, N, L, resampler, 0.5))
+    assert a.sum() == pytest.approx(len(pos), rel=1e-6) and b.sum() == pytest.approx(len(pos), rel=1e-6)
+
+
+def test_mass_soa_odd_mesh_out_of_box(simt, oracle_fast):
+    """N = 45 (no brick edge divides it), SoA columns, masses, positions up to 0.3 L outside the box, shift 0.5."""
+    rng = np.random.default_rng(4)
+    N, L = 45, 250.0
+    pos = (rng.random((9000, 3)) * 1.6 * L - 0.3 * L).astype(np.float32)
+    mass = np.exp(rng.normal(0, 1, len(pos))).astype(np.float32)
+    a, _ = deposit(simt, pos, mass, N, L, "tsc", shift=0.5, soa=True)
+    close(a, oracle_fast.paint(pos, mass, N, L, "tsc", 0.5))
+
+
+def test_float64_positions_cic(simt, oracle_fast):
+    rng = np.random.default_rng(5)
+    N, L = 24, 1.0
+    pos = rng.random((6000, 3)) * L
+    a, _ = deposit(simt, pos, None, N, L, "cic")
+    close(a, oracle_fast.paint(pos, None, N, L, "cic", 0.0))
+
+
+def test_clustered_cells_take_several_chunks(simt, oracle_fast):
+    """7000 particles in one brick (more than the 3072-particle shared-memory chunk), 4000 of them in one cell."""
+    rng = np.random.default_rng(6)
+    N, L = 32, 32.0
+    pos = np.concatenate([rng.random((3000, 3)) * [10.0, 5.0, 20.0] + 1.0, rng.random((4000, 3)) * 0.9 + [3.0, 3.0, 3.0],
+                          rng.random((500, 3)) * L]).astype(np.float32)
+    a, b = deposit(simt, pos, None, N, L, "tsc", pair=True)
+    close(a, oracle_fast.paint(pos, None, N, L, "tsc", 0.0))
+    close(b, oracle_fast.paint(pos, None, N, L, "tsc", 0.5))
+
+
+def test_slab_plan_ignores_foreign_particles(simt, oracle_fast):
+    """Slab [8, 16) of a 32^3 mesh with ghost planes [7 | 8..15 | 16, 17]: only owned particles are deposited."""
+    rng = np.random.default_rng(7)
+    N, L, x0, n0 = 32, 1000.0, 8, 8
+    pos = (rng.random((15000, 3)) * L).astype(np.float32)
+    a, b = deposit(simt, pos, None, N, L, "tsc", pair=True, x0=x0, n0=n0)
+    cell = np.floor(pos[:, 0].astype(np.float64) * N / L).astype(int) % N
+    own = pos[(cell >= x0) & (cell < x0 + n0)]
+    for got, shift in ((a, 0.0), (b, 0.5)):
+        full = oracle_fast.paint(own, None, N, L, "tsc", shift)
+        close(got, full[x0 - 1: x0 + n0 + 2])
+        assert got.sum() == pytest.approx(len(own), rel=1e-6)
+
+
+def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):
+    """Mutation check of the harness itself: without the barrier that separates two shared-memory chunks of a
+    brick, a warp that runs ahead clears the cell lists another warp is still reading.  The scheduler (random warp
+    subsets and single-warp bursts) must turn that into a wrong mesh."""
+    import build_simt
+    src = build_simt.device_part(os.path.join(build_simt.CSRC, "deposit_sorted.cu"))
+    barrier = "if (c0 != pbeg) __syncthreads();"
+    assert src.count(barrier) == 1
+    lib = load(build_simt.compile_kernels(src.replace(barrier, "(void)0;"), str(tmp_path)))
+    rng = np.random.default_rng(3)
+    N, L = 32, 32.0
+    pos = np.concatenate([rng.random((9000, 3)) * L, rng.random((5000, 3)) * [10.0, 5.0, 20.0] + 1.0]).astype(np.float32)
+    got, _ = deposit(lib, pos, None, N, L, "tsc")
+    want = oracle_fast.paint(pos, None, N, L, "tsc", 0.0)
+    assert not np.allclose(got, want, rtol=0, atol=1e-3 * want.max())
