@@ -22,27 +22,61 @@ def device_part(path: str) -> str:
     return text.replace(DYN_SMEM_DECL, "unsigned char *smem_raw = simt::dyn_smem;")
 
 
+def bin_device_part(path: str) -> str:
+    """bin_power.cu without its host launchers; the two inline-PTX RED helpers become plain adds."""
+    text = open(path).read()
+    text = text[:text.index("size_t bin_smem_bytes(int nedges) {")] + "\n}  // namespace apk\n"
+    assert text.count(DYN_SMEM_DECL) == 1
+    text = text.replace(DYN_SMEM_DECL, "unsigned char *smem_raw = simt::dyn_smem;")
+    for ptx in ('asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");',
+                'asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");'):
+        assert text.count(ptx) == 1
+        text = text.replace(ptx, "*addr += v;")
+    return text
+
+
+def _gxx(src: str, inc_dir: str, so: str, extra_flags=()) -> str:
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
+           *extra_flags, "-I", inc_dir, "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+           os.path.join(HERE, src), "-o", so]
+    subprocess.check_call(cmd)
+    return so
+
+
 def compile_kernels(kernel_text: str, out_dir: str, extra_flags=()) -> str:
     """g++ build of deposit_host.cpp around the given device source -> <out_dir>/libapk_simt.so"""
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, "deposit_sorted_kernels.inc"), "w") as f:
         f.write(kernel_text)
-    so = os.path.join(out_dir, "libapk_simt.so")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
-           *extra_flags, "-I", out_dir, "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
-           os.path.join(HERE, "deposit_host.cpp"), "-o", so]
-    subprocess.check_call(cmd)
-    return so
+    return _gxx("deposit_host.cpp", out_dir, os.path.join(out_dir, "libapk_simt.so"), extra_flags)
+
+
+def _fresh(so: str, srcs) -> bool:
+    return os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs)
 
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in ("deposit_sorted.cu", "apk_common.cuh", "deposit_common.cuh")]
     srcs += [os.path.join(HERE, f) for f in ("simt.h", "deposit_host.cpp", "build_simt.py")]
-    if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
+    if not force and _fresh(SO, srcs):
         return SO
     return compile_kernels(device_part(srcs[0]), OUT_DIR)
 
 
+def build_bin(force: bool = False) -> str:
+    """-> tests/simt/_build/libapk_simt_bin.so (bin_power_kernel + bin_fold_kernel on CPU fibers)"""
+    so = os.path.join(OUT_DIR, "libapk_simt_bin.so")
+    srcs = [os.path.join(CSRC, f) for f in ("bin_power.cu", "apk_common.cuh")]
+    srcs += [os.path.join(HERE, f) for f in ("simt.h", "bin_host.cpp", "build_simt.py")]
+    if not force and _fresh(so, srcs):
+        return so
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "bin_power_kernels.inc"), "w") as f:
+        f.write(bin_device_part(srcs[0]))
+    return _gxx("bin_host.cpp", OUT_DIR, so)
+
+
 if __name__ == "__main__":
     print(build(force=True))
+    print(build_bin(force=True))

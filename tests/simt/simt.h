@@ -168,6 +168,7 @@ template <typename T> inline T __shfl_down_sync(unsigned, T v, unsigned d, int =
     const int s = (simt::cur & 31) + (int)d;
     return simt::exchange(v, s < 32 ? s : -1);
 }
+template <typename T> inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return simt::exchange(v, (simt::cur & 31) ^ m); }
 inline unsigned __ballot_sync(unsigned, int pred) {
     const int w = simt::cur >> 5, l = simt::cur & 31;
     simt::wbuf[w][l] = pred ? 1ull : 0ull;
@@ -209,6 +210,7 @@ inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 inline int __double2loint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i & 0xffffffffll); }
 inline int __double2hiint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i >> 32); }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
