@@ -22,6 +22,59 @@ def device_part(path: str) -> str:
     return text.replace(DYN_SMEM_DECL, "unsigned char *smem_raw = simt::dyn_smem;")
 
 
+HOST_MARKS = ("<<<", "APK_CUDA(", "APK_REQUIRE(", "APK_CUFFT(", "set_error(")
+
+
+def strip_host_functions(text: str) -> str:
+    """Drops every top-level definition inside ``namespace apk { ... }`` that is host code (a kernel launch, a CUDA
+    runtime call or an error return) and keeps the kernels, device functions, structs and constants as they are."""
+    ns = text.index("namespace apk {") + len("namespace apk {")
+    head, body = text[:ns], text[ns:]
+    out, chunk, depth, i, n = [], [], 0, 0, len(body)
+    closed = False
+    while i < n:
+        c = body[i]
+        two = body[i:i + 2]
+        if two == "//":
+            j = body.index("\n", i) if "\n" in body[i:] else n
+            chunk.append(body[i:j]); i = j
+            continue
+        if two == "/*":
+            j = body.index("*/", i) + 2
+            chunk.append(body[i:j]); i = j
+            continue
+        if c in "\"'":
+            j = i + 1
+            while body[j] != c:
+                j += 2 if body[j] == "\\" else 1
+            chunk.append(body[i:j + 1]); i = j + 1
+            continue
+        if c == "{":
+            depth += 1
+        elif c == "}":
+            if depth == 0:            # the namespace's own closing brace
+                closed = True
+                break
+            depth -= 1
+        chunk.append(c)
+        i += 1
+        if depth == 0 and c in "};" and (c == ";" or body[i:i + 1] != ";"):
+            piece = "".join(chunk)
+            if not any(m in piece for m in HOST_MARKS):
+                out.append(piece)
+            chunk = []
+    assert closed, "namespace apk is not closed"
+    return head + "".join(out) + "\n}  // namespace apk\n"
+
+
+def misc_device_part() -> str:
+    """Device code of deposit_atomic.cu, route.cu and mesh_ops.cu in one translation unit."""
+    parts = []
+    for f in ("deposit_atomic.cu", "route.cu", "mesh_ops.cu"):
+        parts.append(f"// ---- {f} ----\n" + strip_host_functions(open(os.path.join(CSRC, f)).read()))
+    return "\n".join(parts)
+
+
 def bin_device_part(path: str) -> str:
     """bin_power.cu without its host launchers; the two inline-PTX RED helpers become plain adds."""
     text = open(path).read()
@@ -77,6 +130,21 @@ def build_bin(force: bool = False) -> str:
     return _gxx("bin_host.cpp", OUT_DIR, so)
 
 
+def build_misc(force: bool = False) -> str:
+    """-> tests/simt/_build/libapk_simt_misc.so (direct-atomic deposit, slab routing / transpose / ghost adds,
+    gridded-field helpers on CPU fibers)"""
+    so = os.path.join(OUT_DIR, "libapk_simt_misc.so")
+    srcs = [os.path.join(CSRC, f) for f in ("deposit_atomic.cu", "route.cu", "mesh_ops.cu", "apk_common.cuh", "deposit_common.cuh")]
+    srcs += [os.path.join(HERE, f) for f in ("simt.h", "misc_host.cpp", "build_simt.py")]
+    if not force and _fresh(so, srcs):
+        return so
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "misc_kernels.inc"), "w") as f:
+        f.write(misc_device_part())
+    return _gxx("misc_host.cpp", OUT_DIR, so)
+
+
 if __name__ == "__main__":
     print(build(force=True))
     print(build_bin(force=True))
+    print(build_misc(force=True))
