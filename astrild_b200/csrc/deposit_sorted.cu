@@ -155,7 +155,8 @@ __device__ __forceinline__ AxisBase f32_base(const float *x, const DepositGeom &
 template <int S, bool PAIR>
 __device__ __forceinline__ void f32_finish(const AxisBase &a, float t32, const DepositGeom &G, const BrickGrid &B,
                                            unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3],
-                                           bool &far) {
+                                           bool &far, bool &split) {
+    split = false;
     if (!a.owned) { key0 = key1 = 0xffffffffu; return; }
     const float Nf = (float)G.N;
     float b0[3], b1[3];
@@ -186,32 +187,45 @@ __device__ __forceinline__ void f32_finish(const AxisBase &a, float t32, const D
             const float one = up ? 1.f : 0.f;
             float loc1 = loc + one, bb = b;
             if (loc1 == edge) { loc1 = 0.f; bb = b + 1.f; }
-            if (h + one >= lim) { loc1 = 0.f; bb = 0.f; }          // periodic wrap (slab planes: unreachable)
+            if (h + one >= lim) { loc1 = 0.f; bb = 0.f; split = true; }   // periodic wrap (slab planes: unreachable)
             b1[d] = bb;
             l1[d] = ((S == 2) ? f - 0.5f * one + 0.5f * (1.f - one) : f - one) + loc1;
         }
     }
     key0 = (unsigned int)(int)fmaf(fmaf(b0[0], (float)B.nby, b0[1]), (float)B.nbz, b0[2]);
     key1 = key0;
-    if (PAIR) key1 = (unsigned int)(int)fmaf(fmaf(b1[0], (float)B.nby, b1[1]), (float)B.nbz, b1[2]);
+    if (PAIR) {
+        key1 = (unsigned int)(int)fmaf(fmaf(b1[0], (float)B.nby, b1[1]), (float)B.nbz, b1[2]);
+        split |= key1 != key0;
+    }
 }
 
-// keys and brick-local coordinates of one particle for mesh 0 (G) and, if PAIR, its interlaced twin (G1)
+// keys and brick-local coordinates of one particle for mesh 0 (G) and, if PAIR, its interlaced twin (G1).
+// split: the twin needs a copy of its own -- its home cell lies in another brick, or in the SAME brick but across the
+// periodic boundary (an axis covered by a single brick: N <= 12 / 6 / 30), so that its brick-local coordinate is not
+// mesh 0's plus half a cell.
 template <int S, typename PT, bool PAIR>
 __device__ __forceinline__ void brick_keys(const PT *x, const DepositGeom &G, const DepositGeom &G1, const BrickGrid &B,
-                                           unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3]) {
+                                           unsigned int &key0, float (&l0)[3], unsigned int &key1, float (&l1)[3],
+                                           bool &split) {
     if constexpr (std::is_same<PT, float>::value) {
         if (G.t32 >= 0.f && (!PAIR || G1.t32 >= 0.f) && B.nbricks < (1 << 24)) {
             bool far = false;                        // position more than a box length outside the box (rare)
             const AxisBase a = f32_base(x, G, far);
-            f32_finish<S, PAIR>(a, G.t32, G, B, key0, l0, key1, l1, far);
+            f32_finish<S, PAIR>(a, G.t32, G, B, key0, l0, key1, l1, far, split);
             if (!far) return;
         }
     }
     const double xd[3] = {(double)x[0], (double)x[1], (double)x[2]};
     key0 = brick_of<S>(xd, G, B, l0);
     key1 = key0;
-    if (PAIR) key1 = brick_of<S>(xd, G1, B, l1);
+    split = false;
+    if (PAIR) {
+        key1 = brick_of<S>(xd, G1, B, l1);
+        split = key1 != key0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) split |= fabsf(l1[d] - l0[d] - 0.5f) > 0.25f;
+    }
 }
 
 // raw coordinates of this thread's 4 particles of a tile, v[3*k + d]: slice k of the tile is the
@@ -270,13 +284,14 @@ brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const P
         for (int k = 0; k < 4; ++k) {
             float l[3], l1[3];
             unsigned int key, key1;
-            brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1);
+            bool split;
+            brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1, split);
             if (first + (long long)k * PART_THREADS >= np) key = 0xffffffffu;
             int head, offset, length;
             warp_runs(key, lane, head, offset, length);
             if (key != 0xffffffffu && offset == 0) atomicAdd(counts + key, (unsigned int)length);
             if constexpr (PAIR) {
-                const bool extra = key != 0xffffffffu && key1 != key;
+                const bool extra = key != 0xffffffffu && split;
                 if (__any_sync(0xffffffffu, extra) && extra) atomicAdd(counts + key1, 1u);
             }
         }
@@ -390,7 +405,8 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
                 const long long p = first + (long long)k * PART_THREADS;
                 float l[3], l1[3];
                 unsigned int key, key1;
-                brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1);
+                bool split;
+                brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1, split);
                 if (p >= np) key = 0xffffffffu;
                 live = key != 0xffffffffu;
                 v.x = l[0]; v.y = l[1]; v.z = l[2];
@@ -400,12 +416,12 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
                 }
                 if constexpr (PAIR) {
                     v.x = fmaxf(l[0] + 1.f, 0.f); v.y = fmaxf(l[1] + 1.f, 0.f); v.z = fmaxf(l[2] + 1.f, 0.f);
-                    if (key1 != key) v.y = -v.y;                     // first copy is mesh-0-only
+                    if (split) v.y = -v.y;                           // first copy is mesh-0-only
                 }
                 warp_runs(key, lane, head, offset, length);
                 if (live && offset == 0) slot = atomicAdd(cursor + key, (unsigned int)length);
                 if constexpr (PAIR) {
-                    extra = live && key1 != key;
+                    extra = live && split;
                     if (extra) {                                     // second copy: mesh-1-only, in mesh 1's brick
                         w = v;
                         w.x = -fmaxf(l1[0] + 0.5f, 0.f); w.y = fmaxf(l1[1] + 0.5f, 0.f); w.z = fmaxf(l1[2] + 0.5f, 0.f);

@@ -109,6 +109,21 @@ def test_slab_plan_ignores_foreign_particles(simt, oracle_fast):
         assert got.sum() == pytest.approx(len(own), rel=1e-6)
 
 
+@pytest.mark.parametrize("resampler", ["cic", "tsc"])
+@pytest.mark.parametrize("N,f64", [(6, True), (12, False), (30, False)])
+def test_twin_wrapping_inside_one_brick(simt, oracle_fast, resampler, N, f64):
+    """N <= 30: a single brick spans z (N <= 12 / 6: x / y too), so the shifted twin of a particle in the last cell
+    wraps around the box inside the same brick and must still get a copy of its own (the randomised runs of this
+    harness found that the brick key alone missed it).  Positions include exact cell and half-cell faces."""
+    rng = np.random.default_rng(40 + N)
+    L = 7.3
+    pos = np.concatenate([rng.random((2500, 3)) * 3 * L - L, rng.integers(0, 2 * N + 1, (800, 3)) * 0.5 * L / N])
+    pos = pos.astype(np.float64 if f64 else np.float32)
+    a, b = deposit(simt, pos, None, N, L, resampler, pair=True, soa=f64)
+    close(a, oracle_fast.paint(pos, None, N, L, resampler, 0.0))
+    close(b, oracle_fast.paint(pos, None, N, L, resampler, 0.5))
+
+
 def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):
     """Mutation check of the harness itself: without the barrier that separates two shared-memory chunks of a
     brick, a warp that runs ahead clears the cell lists another warp is still reading.  The scheduler (random warp
