@@ -19,12 +19,13 @@ def test_interlaced_pair_on_single_brick_axes(oracle_fast, resampler, N):
     assert torch.cuda.is_available()
     L = 7.3
     rng = np.random.default_rng(100 + N)
-    pos = np.concatenate([rng.random((30000, 3)) * L,
+    pos = np.concatenate([rng.random((min(30000, 40 * N ** 3), 3)) * L,
                           rng.integers(0, 2 * N + 1, (2000, 3)) * 0.5 * L / N]).astype(np.float32)   # cell / half-cell faces
     eng = ab.get_engine(N, L)
     pair = eng.deposit_pair(pos, None, resampler, method="sorted")
     for mesh, sh in zip(pair, (0.0, 0.5)):
         want = oracle_fast.paint(pos, None, N, L, resampler, sh)
         got = eng.store_mesh(mesh).cpu().numpy()
-        np.testing.assert_allclose(got, want, rtol=0, atol=4e-6 * want.max())
-        assert got.sum() == pytest.approx(len(pos), rel=1e-6)
+        # the defect misplaced ~0.3 of a particle's mass; fp32 accumulation of ~50 particles per cell is ~1e-6
+        np.testing.assert_allclose(got, want, rtol=0, atol=2e-5 * want.max())
+        assert got.sum() == pytest.approx(len(pos), rel=1e-5)
