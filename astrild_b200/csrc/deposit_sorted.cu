@@ -50,13 +50,10 @@ constexpr int DEP_THREADS = 256;                // 8 warps, each owns a 3 x 3 bl
 #ifndef APK_DEP_CTAS
 #define APK_DEP_CTAS 3
 #endif
-#ifndef APK_DEP_PERSISTENT
-#define APK_DEP_PERSISTENT 0      // 1: persistent CTAs pulling bricks from a queue (same speed; blocks stream overlap)
-#endif
+
 constexpr int DEP_CTAS_PER_SM = APK_DEP_CTAS;   // 3: 24 warps per SM at <= 85 registers
 constexpr int CH = 3072;                        // particles per shared-memory chunk
 static_assert(DEP_THREADS / 32 == (BX / 3) * (BY / 3), "one warp per 3 x 3 block of columns");
-constexpr int PPT = CH / DEP_THREADS;           // particles per thread per chunk
 
 struct P3 { float x, y, z; };
 struct P4 { float x, y, z, m; };
@@ -540,6 +537,103 @@ __device__ __forceinline__ bool unpack_pair(VT &v, int sel) {
     return !skip;
 }
 
+// Counting sort of one chunk of <= CHUNK brick-ordered particles by home cell, inside shared memory: cnt[] becomes the
+// exclusive scan of the per-cell counts (cnt[cell] .. cnt[cell + 1] = that cell's particles), sx / sy / sz (/ sm)
+// the brick-local coordinates in cell order.  Called by all threads of the CTA; ends with a barrier.
+template <int S, bool MASS, typename VT, int CHUNK>
+__device__ __forceinline__ void sort_chunk_by_cell(const VT *__restrict__ vals, unsigned int c0, int nchunk, int sel,
+                                                   int *cnt, int *wsum, float *sx, float *sy, float *sz, float *sm) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int OFF = (S == 3) ? 1 : 0;
+    constexpr int PPT = CHUNK / DEP_THREADS;                 // particles per thread per chunk
+    constexpr int NBATCH = PPT % 3 == 0 ? 3 : 2, BATCH = PPT / NBATCH;   // loads are issued BATCH at a time before first use
+    static_assert(BATCH * NBATCH == PPT && PPT * DEP_THREADS == CHUNK, "chunk size must divide into the load batches");
+    for (int i = tid; i <= BRICK_CELLS; i += DEP_THREADS) cnt[i] = 0;
+    __syncthreads();
+
+    // ---- rank my particles inside their home cell (cell | rank << 13 kept in a register;
+    //      the coordinates are re-read from L1/L2 in the scatter pass to save registers).
+    //      Loads are issued in batches before first use to overlap their latency.
+    int packed[PPT];
+#pragma unroll
+    for (int h = 0; h < NBATCH; ++h) {
+        VT v[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = (h * BATCH + k) * DEP_THREADS + tid;
+            v[k] = vals[c0 + min(i, nchunk - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = (h * BATCH + k) * DEP_THREADS + tid;
+            const bool keep = unpack_pair(v[k], sel);
+            int hx, hy, hz;
+            if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
+            else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
+            hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BrickZ<S>::CELLS - 1));
+            const int cell = (hx * BY + hy) * BZ + hz + OFF;          // z-lane = home z + OFF
+            packed[h * BATCH + k] = -1;
+            if (i < nchunk && keep) packed[h * BATCH + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
+        }
+    }
+    __syncthreads();
+
+    // ---- exclusive scan of the cell counts (9 per thread) ------------------------
+    {
+        constexpr int PER = BRICK_CELLS / DEP_THREADS;
+        static_assert(PER * DEP_THREADS == BRICK_CELLS, "cells must divide evenly among the threads");
+        int v[PER], s = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = cnt[tid * PER + k]; s += v[k]; }
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < DEP_THREADS / 32 ? wsum[lane] : 0;
+            int wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            wsum[32 + lane] = wi - w;   // exclusive warp offsets
+        }
+        __syncthreads();
+        int run = wsum[32 + warp] + incl - s;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { cnt[tid * PER + k] = run; run += v[k]; }
+        if (tid == DEP_THREADS - 1) cnt[BRICK_CELLS] = run;
+    }
+    __syncthreads();
+
+    // ---- scatter into cell order --------------------------------------------------
+#pragma unroll
+    for (int h = 0; h < NBATCH; ++h) {
+        VT v[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = (h * BATCH + k) * DEP_THREADS + tid;
+            v[k] = vals[c0 + min(i, nchunk - 1)];
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int pk = packed[h * BATCH + k];
+            if (pk >= 0) {
+                unpack_pair(v[k], sel);
+                const int slot = cnt[pk & 8191] + (pk >> 13);
+                sx[slot] = v[k].x; sy[slot] = v[k].y; sz[slot] = v[k].z;
+                if constexpr (MASS) sm[slot] = v[k].m;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int S, bool MASS, typename VT>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM)
 brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
@@ -553,41 +647,16 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     float *sy = sx + CH;
     float *sz = sy + CH;
     float *sm = sz + CH;                                          // only if MASS
-#if APK_DEP_PERSISTENT
-    __shared__ unsigned int s_info[3];
-#endif
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     constexpr int OFF = (S == 3) ? 1 : 0;   // window origin = home cell - OFF
-    constexpr int NBATCH = 3, BATCH = PPT / NBATCH;   // loads are issued BATCH at a time before first use
-    static_assert(BATCH * NBATCH == PPT, "PPT must divide into the load batches");
     constexpr int W = 3 + S - 1;            // edge of a warp's private window: its 3 columns + halo
     // this warp's 3 x 3 block of (x,y) columns inside the brick
     const int bi = warp / (BY / 3), bj = warp % (BY / 3);
 
     const unsigned int nfilled = *nfilled_ptr;
-#if APK_DEP_PERSISTENT
-    // Work queue over the list of non-empty bricks: thread 0 claims the NEXT entry while the current brick is
-    // processed.  The dependent round trips (queue counter -> brick id -> the brick's particle range) are
-    // spread over the sort phases so that no warp waits for them; the result is published in s_info before
-    // the moments phase.
-    if (tid == 0) {
-        const unsigned int i0 = atomicAdd(work_counter, 1u);
-        const unsigned int b0 = i0 < nfilled ? filled[i0] : (unsigned)B.nbricks;
-        s_info[0] = b0;
-        s_info[1] = b0 < (unsigned)B.nbricks ? brick_start[b0] : 0u;
-        s_info[2] = b0 < (unsigned)B.nbricks ? brick_start[b0 + 1] : 0u;
-    }
-
-    for (;;) {
-        __syncthreads();
-        const unsigned int brick = s_info[0], pbeg = s_info[1], pend = s_info[2];
-        if (brick >= (unsigned)B.nbricks) break;
-        unsigned int ni = 0, nb = (unsigned)B.nbricks, nbeg = 0, nend = 0;
-        if (tid == 0) ni = atomicAdd(work_counter, 1u);
-#else
     // One CTA per non-empty brick, in list order (x-major: neighbouring windows meet in L2).  CTAs retire
     // all the time, so kernels of a higher-priority stream (the slab path's FFT / transpose of the first mesh)
     // get SMs while this one runs; a persistent grid would hold every register file until it ends.
@@ -595,7 +664,6 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
         if (slot != blockIdx.x) __syncthreads();
         const unsigned int brick = filled[slot];
         const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
-#endif
 
         const int bz = brick % B.nbz;
         const int by = (brick / B.nbz) % B.nby;
@@ -604,99 +672,7 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
         for (unsigned int c0 = pbeg; c0 < pend; c0 += CH) {
             const int nchunk = (int)min((unsigned int)CH, pend - c0);
             if (c0 != pbeg) __syncthreads();   // every warp is done with the previous chunk's lists
-            for (int i = tid; i <= BRICK_CELLS; i += DEP_THREADS) cnt[i] = 0;
-            __syncthreads();
-
-            // ---- rank my particles inside their home cell (cell | rank << 13 kept in a register;
-            //      the coordinates are re-read from L1/L2 in the scatter pass to save registers).
-            //      Loads are issued in batches before first use to overlap their latency.
-            int packed[PPT];
-#pragma unroll
-            for (int h = 0; h < NBATCH; ++h) {
-                VT v[BATCH];
-#pragma unroll
-                for (int k = 0; k < BATCH; ++k) {
-                    const int i = (h * BATCH + k) * DEP_THREADS + tid;
-                    v[k] = vals[c0 + min(i, nchunk - 1)];
-                }
-#pragma unroll
-                for (int k = 0; k < BATCH; ++k) {
-                    const int i = (h * BATCH + k) * DEP_THREADS + tid;
-                    const bool keep = unpack_pair(v[k], sel);
-                    int hx, hy, hz;
-                    if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
-                    else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
-                    hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BrickZ<S>::CELLS - 1));
-                    const int cell = (hx * BY + hy) * BZ + hz + OFF;          // z-lane = home z + OFF
-                    packed[h * BATCH + k] = -1;
-                    if (i < nchunk && keep) packed[h * BATCH + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
-                }
-            }
-            __syncthreads();
-#if APK_DEP_PERSISTENT
-            if (tid == 0 && c0 == pbeg && ni < nfilled) nb = filled[ni];
-#endif
-
-            // ---- exclusive scan of the cell counts (9 per thread) ------------------------
-            {
-                constexpr int PER = BRICK_CELLS / DEP_THREADS;
-                static_assert(PER * DEP_THREADS == BRICK_CELLS, "cells must divide evenly among the threads");
-                int v[PER], s = 0;
-#pragma unroll
-                for (int k = 0; k < PER; ++k) { v[k] = cnt[tid * PER + k]; s += v[k]; }
-                int incl = s;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                if (lane == 31) wsum[warp] = incl;
-                __syncthreads();
-                if (warp == 0) {
-                    int w = lane < DEP_THREADS / 32 ? wsum[lane] : 0;
-                    int wi = w;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, wi, o);
-                        if (lane >= o) wi += t;
-                    }
-                    wsum[32 + lane] = wi - w;   // exclusive warp offsets
-                }
-                __syncthreads();
-                int run = wsum[32 + warp] + incl - s;
-#pragma unroll
-                for (int k = 0; k < PER; ++k) { cnt[tid * PER + k] = run; run += v[k]; }
-                if (tid == DEP_THREADS - 1) cnt[BRICK_CELLS] = run;
-            }
-            __syncthreads();
-#if APK_DEP_PERSISTENT
-            if (tid == 0 && c0 == pbeg && nb < (unsigned)B.nbricks) { nbeg = brick_start[nb]; nend = brick_start[nb + 1]; }
-#endif
-
-            // ---- scatter into cell order --------------------------------------------------
-#pragma unroll
-            for (int h = 0; h < NBATCH; ++h) {
-                VT v[BATCH];
-#pragma unroll
-                for (int k = 0; k < BATCH; ++k) {
-                    const int i = (h * BATCH + k) * DEP_THREADS + tid;
-                    v[k] = vals[c0 + min(i, nchunk - 1)];
-                }
-#pragma unroll
-                for (int k = 0; k < BATCH; ++k) {
-                    const int pk = packed[h * BATCH + k];
-                    if (pk >= 0) {
-                        unpack_pair(v[k], sel);
-                        const int slot = cnt[pk & 8191] + (pk >> 13);
-                        sx[slot] = v[k].x; sy[slot] = v[k].y; sz[slot] = v[k].z;
-                        if constexpr (MASS) sm[slot] = v[k].m;
-                    }
-                }
-            }
-#if APK_DEP_PERSISTENT
-            if (tid == 0 && c0 == pbeg) { s_info[0] = nb; s_info[1] = nbeg; s_info[2] = nend; }
-#endif
-            __syncthreads();
+            sort_chunk_by_cell<S, MASS, VT, CH>(vals, c0, nchunk, sel, cnt, wsum, sx, sy, sz, sm);
 
             // ---- moments per home cell; each warp walks its own 9 columns, no CTA barrier ----
             // lane = z-cell of the column (home z + OFF), so the z-spread is two shuffles: every lane
@@ -833,9 +809,8 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     int per_sm = 1;
     APK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEP_THREADS, smem));
     if (per_sm < 1) per_sm = 1;
-    // persistent: one wave; otherwise one CTA per brick (CTAs beyond the number of non-empty bricks, which only
-    // the device knows, exit at once)
-    const int ctas = APK_DEP_PERSISTENT ? std::min(P->num_sms * per_sm, B.nbricks) : B.nbricks;
+    // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
+    const int ctas = B.nbricks;
     P->mark(3, st);
     kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G, B, counter, mesh, PAIR ? 0 : -1);
     APK_CUDA(cudaGetLastError());
