@@ -446,83 +446,74 @@ struct DepSmem {
 };
 
 // Window moments of the particles of one home cell, accumulated with packed FFMA2.
-// Layout: A[a][c] = float2 over the b-pair (first, last) of the window, Bm[a][c] = middle b (TSC only).
+// Layout: A[a][c] = float2 over the b-pair (first, last) of the window; for TSC the middle b is kept as
+// B2[a] = float2 over the c-pair (first, last) and B1[a] = the centre (b = c = middle): 27 moments in 12 packed and 3
+// scalar accumulators, 15 FMA instructions per particle.  The per-axis weights are formed the same way, the two outer
+// ones of an axis as one float2: 0.5 (0.5 -+ d)^2 = (s/2 -+ s d)^2 with s = sqrt(1/2).
 template <int S, bool MASS>
 struct Moments {
     float2 A[S][S];
-    float Bm[S][S];   // unused for S == 2
+    float2 B2[S];     // TSC only
+    float B1[S];      // TSC only
 
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int a = 0; a < S; ++a)
-#pragma unroll
-            for (int c = 0; c < S; ++c) { A[a][c] = make_float2(0.f, 0.f); Bm[a][c] = 0.f; }
-    }
-
-    // per-axis window weights of one particle: x and z as scalars, y packed as (first, last) + middle
-    __device__ __forceinline__ static void weights(float dx, float dy, float dz, float m, float (&wx)[S],
-                                                   float2 &wyp, float &wym, float (&wz)[S]) {
-        wym = 0.f;
+    // outer weights of one axis as a pair (first, last), and the middle one (TSC; CIC has no middle)
+    __device__ __forceinline__ static void axis(float d, float2 &wp, float &wm) {
         if (S == 2) {
-            wx[0] = 1.f - dx; wx[S - 1] = dx;
-            wz[0] = 1.f - dz; wz[S - 1] = dz;
-            wyp = make_float2(1.f - dy, dy);
+            wp = make_float2(1.f - d, d);
+            wm = 0.f;
         } else {
-            const float c = 0.70710678118654752f;   // sqrt(1/2): 0.5 (0.5 -+ d)^2 = (c/2 -+ c d)^2
-            const float x0 = fmaf(-c, dx, 0.5f * c), x2 = fmaf(c, dx, 0.5f * c);
-            wx[0] = x0 * x0; wx[S / 2] = fmaf(-dx, dx, 0.75f); wx[S - 1] = x2 * x2;
-            const float z0 = fmaf(-c, dz, 0.5f * c), z2 = fmaf(c, dz, 0.5f * c);
-            wz[0] = z0 * z0; wz[S / 2] = fmaf(-dz, dz, 0.75f); wz[S - 1] = z2 * z2;
-            const float2 ty = __ffma2_rn(make_float2(-c, c), make_float2(dy, dy), make_float2(0.5f * c, 0.5f * c));
-            wyp = __fmul2_rn(ty, ty);
-            wym = fmaf(-dy, dy, 0.75f);
-        }
-        if (MASS) {
-#pragma unroll
-            for (int a = 0; a < S; ++a) wx[a] *= m;
+            const float s = 0.70710678118654752f;
+            const float2 t = __ffma2_rn(make_float2(-s, s), make_float2(d, d), make_float2(0.5f * s, 0.5f * s));
+            wp = __fmul2_rn(t, t);
+            wm = fmaf(-d, d, 0.75f);
         }
     }
 
-    __device__ __forceinline__ void add(float dx, float dy, float dz, float m) {
-        float wx[S], wz[S], wym;
-        float2 wyp;
-        weights(dx, dy, dz, m, wx, wyp, wym, wz);
+    // FIRST: the particle sets the moments (no zeroing pass); otherwise it is added.  !valid (FIRST only): the cell
+    // is empty and everything becomes zero; its coordinates are whatever the list holds at that slot, hence the selects.
+    template <bool FIRST>
+    __device__ __forceinline__ void put(float dx, float dy, float dz, float m, bool valid) {
+        float2 wxp, wyp, wzp;
+        float wxm, wym, wzm;
+        axis(FIRST && !valid ? 0.f : dx, wxp, wxm);
+        axis(FIRST && !valid ? 0.f : dy, wyp, wym);
+        axis(FIRST && !valid ? 0.f : dz, wzp, wzm);
+        if (MASS) { wxp = __fmul2_rn(wxp, make_float2(m, m)); wxm *= m; }
+        if (FIRST && !valid) { wxp = make_float2(0.f, 0.f); wxm = 0.f; }
+        const float wx[3] = {wxp.x, wxm, wxp.y};              // index S - 1 of CIC is .y
+        const float wz[3] = {wzp.x, wzm, wzp.y};
 #pragma unroll
         for (int a = 0; a < S; ++a) {
-            const float2 wxy = __fmul2_rn(make_float2(wx[a], wx[a]), wyp);
-            const float wxm = wx[a] * wym;
-#pragma unroll
-            for (int c = 0; c < S; ++c) {
-                A[a][c] = __ffma2_rn(wxy, make_float2(wz[c], wz[c]), A[a][c]);
-                if (S == 3) Bm[a][c] = fmaf(wxm, wz[c], Bm[a][c]);
-            }
-        }
-    }
-
-    // the first particle of a cell sets the moments (no zeroing pass); !valid: the cell is empty, all zero.
-    // The coordinates of an empty cell are whatever the list holds at that slot, hence the selects.
-    __device__ __forceinline__ void init(float dx, float dy, float dz, float m, bool valid) {
-        float wx[S], wz[S], wym;
-        float2 wyp;
-        weights(valid ? dx : 0.f, valid ? dy : 0.f, valid ? dz : 0.f, m, wx, wyp, wym, wz);
-#pragma unroll
-        for (int a = 0; a < S; ++a) {
-            const float w = valid ? wx[a] : 0.f;
+            const float w = (a == S - 1) ? wx[2] : wx[a];
             const float2 wxy = __fmul2_rn(make_float2(w, w), wyp);
-            const float wxm = w * wym;
 #pragma unroll
             for (int c = 0; c < S; ++c) {
-                A[a][c] = __fmul2_rn(wxy, make_float2(wz[c], wz[c]));
-                Bm[a][c] = (S == 3) ? wxm * wz[c] : 0.f;
+                const float z = (c == S - 1) ? wz[2] : wz[c];
+                A[a][c] = FIRST ? __fmul2_rn(wxy, make_float2(z, z)) : __ffma2_rn(wxy, make_float2(z, z), A[a][c]);
+            }
+        }
+        if (S == 3) {
+            const float2 mp = __fmul2_rn(wxp, make_float2(wym, wym));      // (wx0 wym, wx2 wym)
+            const float mm = wxm * wym;
+            const float wm[3] = {mp.x, mm, mp.y};
+#pragma unroll
+            for (int a = 0; a < S; ++a) {
+                B2[a] = FIRST ? __fmul2_rn(make_float2(wm[a], wm[a]), wzp) : __ffma2_rn(make_float2(wm[a], wm[a]), wzp, B2[a]);
+                B1[a] = FIRST ? wm[a] * wzm : fmaf(wm[a], wzm, B1[a]);
             }
         }
     }
+
+    __device__ __forceinline__ void add(float dx, float dy, float dz, float m) { put<false>(dx, dy, dz, m, true); }
+    __device__ __forceinline__ void init(float dx, float dy, float dz, float m, bool valid) { put<true>(dx, dy, dz, m, valid); }
 
     // moment of window offset (a, b, c)
     __device__ __forceinline__ float get(int a, int b, int c) const {
         if (b == 0) return A[a][c].x;
         if (b == S - 1) return A[a][c].y;
-        return Bm[a][c];
+        if (c == 0) return B2[a].x;
+        if (c == S - 1) return B2[a].y;
+        return B1[a];
     }
 };
 
