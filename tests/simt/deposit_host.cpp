@@ -104,3 +104,24 @@ extern "C" long long simt_deposit_sorted(const void *p0, const void *p1, const v
     }
     return simt::switches;
 }
+
+// brick_keys for every particle (float32 positions, whole-mesh plan): keys, brick-local coordinates and the split
+// flag of the interlaced pair, for a direct check of the float-register index arithmetic at large mesh sizes.
+extern "C" void simt_brick_keys(const float *xyz, long long np, int N, double pos_scale, int resampler,
+                                unsigned int *key0, unsigned int *key1, float *l0, float *l1, int *split, int *grid) {
+    const DepositGeom G = make_geom(N, pos_scale, 0.0, resampler, 0, N, 1, 2);
+    DepositGeom G1 = G;
+    G1.shift = 0.5;
+    G1.t32 = G.t32 + 0.5f;
+    const int S = resampler == APK_CIC ? 2 : 3;
+    const BrickGrid B = make_brick_grid(G, S);
+    grid[0] = B.nbx; grid[1] = B.nby; grid[2] = B.nbz;
+    for (long long p = 0; p < np; ++p) {
+        float a[3], b[3];
+        bool sp;
+        if (S == 2) brick_keys<2, float, true>(xyz + 3 * p, G, G1, B, key0[p], a, key1[p], b, sp);
+        else brick_keys<3, float, true>(xyz + 3 * p, G, G1, B, key0[p], a, key1[p], b, sp);
+        for (int d = 0; d < 3; ++d) { l0[3 * p + d] = a[d]; l1[3 * p + d] = b[d]; }
+        split[p] = sp;
+    }
+}

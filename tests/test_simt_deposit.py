@@ -124,6 +124,50 @@ def test_twin_wrapping_inside_one_brick(simt, oracle_fast, resampler, N, f64):
     close(b, oracle_fast.paint(pos, None, N, L, resampler, 0.5))
 
 
+@pytest.mark.parametrize("resampler", ["cic", "tsc"])
+@pytest.mark.parametrize("N", [1024, 2048, 1000])
+def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, N):
+    """The partition's index arithmetic stays in float32 registers (cells up to 2047, bricks up to 341, no integer
+    division): checked for every particle against integer arithmetic on the float64 grid coordinate -- home cell,
+    brick, brick-local coordinate of both interlaced twins and the rule for the twin's own copy."""
+    rng = np.random.default_rng(N)
+    n = 200000
+    pos = rng.random((n, 3))
+    pos[:20000] = rng.integers(0, 2 * N, (20000, 3)) * (0.5 / N) + rng.normal(0, 1e-5, (20000, 3))   # around cell faces
+    pos[20000:22000] = rng.random((2000, 3)) * 3 - 1                                               # outside the box
+    pos = pos.astype(np.float32)
+    simt.simt_brick_keys.restype = None
+    simt.simt_brick_keys.argtypes = [ct.c_void_p, ct.c_longlong, ct.c_int, ct.c_double, ct.c_int] + [ct.c_void_p] * 6
+    key0, key1 = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    l0, l1 = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
+    split, grid = np.zeros(n, np.int32), np.zeros(3, np.int32)
+    simt.simt_brick_keys(pos.ctypes.data, n, N, 1.0, {"cic": 2, "tsc": 3}[resampler], key0.ctypes.data, key1.ctypes.data,
+                         l0.ctypes.data, l1.ctypes.data, split.ctypes.data, grid.ctypes.data)
+    edge = np.array([12, 6, 30 if resampler == "tsc" else 31])
+    g = pos.astype(np.float64) * N                               # pos_scale = 1: Ramses-style coordinates
+    clear = np.abs(g * 2 - np.round(g * 2)).min(axis=1) > 1e-9   # not within rounding of a cell / half-cell face
+    round_up = 0.5 if resampler == "tsc" else 0.0
+
+    def expect(shift):
+        home = np.floor(g + shift + round_up).astype(np.int64)
+        frac = g + shift - home                                   # relative to the home cell
+        cell = home % N
+        brick = cell // edge
+        key = (brick[:, 0] * grid[1] + brick[:, 1]) * grid[2] + brick[:, 2]
+        return key, cell - brick * edge + frac, cell, brick
+
+    k0, c0, cell0, b0 = expect(0.0)
+    k1, c1, cell1, b1 = expect(0.5)
+    np.testing.assert_array_equal(key0[clear], k0[clear])
+    np.testing.assert_array_equal(key1[clear], k1[clear])
+    np.testing.assert_allclose(l0[clear], c0[clear], rtol=0, atol=3e-4)      # float32 positions at |g| ~ 2000
+    np.testing.assert_allclose(l1[clear], c1[clear], rtol=0, atol=3e-4)
+    # the twin shares mesh 0's copy exactly when it sits in the same brick at mesh 0's coordinate + half a cell
+    own_copy = (k1 != k0) | (np.abs(c1 - c0 - 0.5) > 0.25).any(axis=1)
+    np.testing.assert_array_equal(split[clear].astype(bool), own_copy[clear])
+    assert split.mean() < 0.25
+
+
 def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):
     """Mutation check of the harness itself: without the barrier that separates two shared-memory chunks of a
     brick, a warp that runs ahead clears the cell lists another warp is still reading.  The scheduler (random warp
