@@ -36,6 +36,8 @@
 #include "deposit_common.cuh"
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 namespace apk {
@@ -629,8 +631,7 @@ template <int S, bool MASS, typename VT>
 __global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM)
 brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
                      const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
-                     DepositGeom G, BrickGrid B, unsigned int *__restrict__ work_counter,
-                     float *__restrict__ mesh, int sel) {
+                     DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int *cnt = reinterpret_cast<int *>(smem_raw);                 // [BRICK_CELLS + 1]
     int *wsum = cnt + BRICK_CELLS + 1;                            // [64] scan scratch
@@ -735,6 +736,122 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Particle-parallel tile kernel (unit masses): one THREAD per particle, the brick's window of the mesh lives in shared
+// memory as 32-bit FIXED-POINT integers and every one of the S^3 weights goes there with a native integer ATOMS.ADD
+// (shared-memory float atomics are CAS loops on sm_100; integer adds are not).  No in-brick sort, no per-cell loop:
+// all 32 lanes work on every instruction, whatever the cell occupancy.
+//   quantum 2^-PP_FRAC_BITS of a particle's mass; a weight is rounded to it by ONE FFMA against a magic constant
+//   (1.5 * 2^(23 - PP_FRAC_BITS): the sum lands in a binade whose ulp is the quantum, so the low mantissa bits ARE the
+//   fixed-point value); at most PP_FLUSH particles are accumulated between two flushes, so that a cell cannot
+//   overflow 32 bits even if every one of them sits in it.  Integer adds commute: a brick's contribution to the mesh
+//   does not depend on the order in which the partition filed its particles.
+//   The tile goes to the mesh as before: one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
+constexpr int PP_FRAC_BITS = 20;
+constexpr int PP_FLUSH = 4095;                        // particles between two flushes: 4095 * 2^20 < 2^32
+constexpr int PP_THREADS = 256;
+#ifndef APK_PP_CTAS
+#define APK_PP_CTAS 6
+#endif
+
+template <int S> struct PPTile {
+    static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
+    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ;
+    static constexpr int CELLS = TX * TY * TZ;
+};
+
+// nearest brick-local home cell of coordinate l on one axis (clamped to the brick) as float and int, and the offset
+// d = l - home: [-0.5, 0.5] for TSC, [0, 1] for CIC (ties land on either side; the windows are continuous there)
+template <int S>
+__device__ __forceinline__ void pp_home(float l, float last, float &d, int &h) {
+    const float M = 12582912.f;                       // 1.5 * 2^23: adding it rounds to the nearest integer
+    float t = (S == 2 ? l - 0.5f : l) + M;
+    t = fminf(fmaxf(t, M), M + last);
+    h = __float_as_int(t) & 0x3fffff;
+    d = l - (t - M);
+}
+
+template <int S, typename VT>
+__global__ void __launch_bounds__(PP_THREADS, APK_PP_CTAS)
+brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
+                        const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
+                        DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
+    using T = PPTile<S>;
+    __shared__ unsigned int tile[T::CELLS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int nfilled = *nfilled_ptr;
+    const float magic = 1.5f * (float)(1 << (23 - PP_FRAC_BITS));
+    const unsigned int magic_bits = (unsigned int)__float_as_int(magic);
+    const float quantum = 1.f / (float)(1 << PP_FRAC_BITS);
+
+    for (unsigned int slot = blockIdx.x; slot < nfilled; slot += gridDim.x) {
+        const unsigned int brick = filled[slot];
+        const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
+        const int bz = brick % B.nbz;
+        const int by = (brick / B.nbz) % B.nby;
+        const int bx = brick / (B.nbz * B.nby);
+
+        for (int i = tid; i < T::CELLS; i += PP_THREADS) tile[i] = 0u;
+        __syncthreads();
+
+        for (unsigned int c0 = pbeg; c0 < pend; c0 += PP_FLUSH) {
+            const unsigned int c1 = min(c0 + (unsigned int)PP_FLUSH, pend);
+            // ---- one thread per particle; the next particle's loads are in flight while this one is deposited ----
+            unsigned int p = c0 + tid;
+            VT nxt = {};
+            if (p < c1) nxt = vals[p];
+            for (; p < c1; p += PP_THREADS) {
+                VT v = nxt;
+                if (p + PP_THREADS < c1) nxt = vals[p + PP_THREADS];
+                if (!unpack_pair(v, sel)) continue;
+                float dx, dy, dz;
+                int hx, hy, hz;
+                pp_home<S>(v.x, (float)(BX - 1), dx, hx);
+                pp_home<S>(v.y, (float)(BY - 1), dy, hy);
+                pp_home<S>(v.z, (float)(BrickZ<S>::CELLS - 1), dz, hz);
+                float wx[S], wy[S], wz[S];
+                if (S == 2) {
+                    wx[0] = 1.f - dx; wx[S - 1] = dx; wy[0] = 1.f - dy; wy[S - 1] = dy; wz[0] = 1.f - dz; wz[S - 1] = dz;
+                } else {
+                    const float ax = 0.5f - dx, cx = 0.5f + dx, ay = 0.5f - dy, cy = 0.5f + dy, az = 0.5f - dz, cz = 0.5f + dz;
+                    wx[0] = 0.5f * ax * ax; wx[S / 2] = fmaf(-dx, dx, 0.75f); wx[S - 1] = 0.5f * cx * cx;
+                    wy[0] = 0.5f * ay * ay; wy[S / 2] = fmaf(-dy, dy, 0.75f); wy[S - 1] = 0.5f * cy * cy;
+                    wz[0] = 0.5f * az * az; wz[S / 2] = fmaf(-dz, dz, 0.75f); wz[S - 1] = 0.5f * cz * cz;
+                }
+                unsigned int *cell = tile + (hx * T::TY + hy) * T::TZ + hz;     // window origin (home - OFF) in tile coordinates
+#pragma unroll
+                for (int a = 0; a < S; ++a)
+#pragma unroll
+                    for (int b = 0; b < S; ++b) {
+                        const float wxy = wx[a] * wy[b];
+#pragma unroll
+                        for (int c = 0; c < S; ++c) {
+                            const unsigned int q = (unsigned int)__float_as_int(fmaf(wxy, wz[c], magic)) - magic_bits;
+                            atomicAdd(cell + (a * T::TY + b) * T::TZ + c, q);
+                        }
+                    }
+            }
+            __syncthreads();   // every particle of the chunk is in the tile
+
+            // ---- tile -> mesh: one coalesced 128-byte RED per (x,y) column, zeros skipped; the tile is cleared on the way ----
+            const int gz = wrap_index32(bz * BrickZ<S>::CELLS - T::OFF + lane, G.N);
+            const int x0 = bx * BX - T::OFF, y0 = by * BY - T::OFF;
+            for (int col = warp; col < T::TX * T::TY; col += PP_THREADS / 32) {
+                const int u = col / T::TY, w = col - u * T::TY;
+                const unsigned int q = tile[col * T::TZ + lane];
+                if (c1 < pend) tile[col * T::TZ + lane] = 0u;
+                int px = x0 + u;
+                bool ok = true;
+                if (G.slab) ok = px >= 0 && px < G.nplanes;
+                else px = wrap_index32(px, G.N);
+                if (ok && q != 0u)
+                    atomicAdd(mesh + ((long long)px * G.N + wrap_index32(y0 + w, G.N)) * G.ldz + gz, (float)q * quantum);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 static size_t max_bricks(const apk_plan *P) {
     return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + 29) / 30);
 }
@@ -774,7 +891,7 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     unsigned int *filled = (unsigned int *)w; w += tab;
     unsigned int *seg_total = (unsigned int *)w; w += align256(4 * (max_bricks(P) / SCAN_SEG + 2));
     unsigned int *seg_filled = (unsigned int *)w; w += align256(4 * (max_bricks(P) / SCAN_SEG + 2));
-    unsigned int *counter = (unsigned int *)w;          // [0] work queue, [1] number of non-empty bricks
+    unsigned int *counter = (unsigned int *)w;          // [1] number of non-empty bricks
 
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)P->num_sms * 8);
@@ -792,24 +909,33 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT><<<pb, PART_THREADS, 0, st>>>(
         (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, G1, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
-    APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
 
-    auto kern = brick_deposit_kernel<S, MASS, VT>;
-    const size_t smem = DepSmem<MASS>::bytes;
-    APK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    APK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DEP_THREADS, smem));
-    if (per_sm < 1) per_sm = 1;
-    // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
-    const int ctas = B.nbricks;
+    // unit masses: particle-parallel fixed-point tile kernel; with masses: the per-cell register-moment kernel
+    static const bool force_cell = [] { const char *e = getenv("APK_TILE_KERNEL"); return e && !strcmp(e, "cell"); }();
+    const int ctas = B.nbricks;     // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
     P->mark(3, st);
-    kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G, B, counter, mesh, PAIR ? 0 : -1);
-    APK_CUDA(cudaGetLastError());
-    if (PAIR) {
-        if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
-        APK_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-        kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G1, B, counter, mesh1, 1);
+    if (!MASS && !force_cell) {
+        if constexpr (!MASS) {
+            auto kern = brick_deposit_pp_kernel<S, VT>;
+            kern<<<ctas, PP_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, PAIR ? 0 : -1);
+            APK_CUDA(cudaGetLastError());
+            if (PAIR) {
+                if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
+                kern<<<ctas, PP_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G1, B, mesh1, 1);
+                APK_CUDA(cudaGetLastError());
+            }
+        }
+    } else {
+        auto kern = brick_deposit_kernel<S, MASS, VT>;
+        const size_t smem = DepSmem<MASS>::bytes;
+        APK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, PAIR ? 0 : -1);
         APK_CUDA(cudaGetLastError());
+        if (PAIR) {
+            if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
+            kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G1, B, mesh1, 1);
+            APK_CUDA(cudaGetLastError());
+        }
     }
     P->mark(4, st);
     if (P->timing) { P->dep_timed = true; P->dep_sorted = true; }

@@ -14,6 +14,8 @@ using namespace apk;
 
 namespace {
 
+int g_force_cell_kernel = 0;     // simt_force_cell_kernel(1): unit masses through the per-cell kernel too
+
 DepositGeom make_geom(int N, double pos_scale, double shift, int resampler, int x0, int n0, int ghost_lo, int ghost_hi) {
     DepositGeom G;
     G.N = N; G.ldz = 2 * (N / 2 + 1); G.scale = pos_scale * (double)N; G.shift = shift;
@@ -59,16 +61,26 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
         brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
                                                         G1, B, cursor.data(), vals.data());
     });
-    counter[0] = 0;
-    simt::launch(B.nbricks, DEP_THREADS, [&] {
-        brick_deposit_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, counter, mesh, PAIR ? 0 : -1);
-    });
-    if (PAIR) {
-        counter[0] = 0;
-        simt::launch(B.nbricks, DEP_THREADS, [&] {
-            brick_deposit_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, counter, mesh1, 1);
-        });
+    // the launcher's choice (run_sorted): unit masses -> particle-parallel fixed-point tile kernel, masses -> per-cell kernel
+    if (!MASS && !g_force_cell_kernel) {
+        if constexpr (!MASS) {
+            simt::launch(B.nbricks, PP_THREADS, [&] {
+                brick_deposit_pp_kernel<S, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, PAIR ? 0 : -1);
+            });
+            if (PAIR)
+                simt::launch(B.nbricks, PP_THREADS, [&] {
+                    brick_deposit_pp_kernel<S, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, mesh1, 1);
+                });
+        }
+        return;
     }
+    simt::launch(B.nbricks, DEP_THREADS, [&] {
+        brick_deposit_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, PAIR ? 0 : -1);
+    });
+    if (PAIR)
+        simt::launch(B.nbricks, DEP_THREADS, [&] {
+            brick_deposit_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, mesh1, 1);
+        });
 }
 
 template <int S, typename PT, bool SOA>
@@ -104,6 +116,8 @@ extern "C" long long simt_deposit_sorted(const void *p0, const void *p1, const v
     }
     return simt::switches;
 }
+
+extern "C" void simt_force_cell_kernel(int on) { g_force_cell_kernel = on; }
 
 // brick_keys for every particle (float32 positions, whole-mesh plan): keys, brick-local coordinates and the split
 // flag of the interlaced pair, for a direct check of the float-register index arithmetic at large mesh sizes.

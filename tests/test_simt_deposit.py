@@ -169,12 +169,12 @@ def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, N):
 
 
 def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):
-    """Mutation check of the harness itself: without the barrier that separates two shared-memory chunks of a
-    brick, a warp that runs ahead clears the cell lists another warp is still reading.  The scheduler (random warp
-    subsets and single-warp bursts) must turn that into a wrong mesh."""
+    """Mutation check of the harness itself: without the barrier between the particle loop and the flush of the
+    particle-parallel tile kernel, a warp that runs ahead sends (and clears) tile cells other warps are still adding to.
+    The scheduler (random warp subsets and single-warp bursts) must turn that into a wrong mesh."""
     import build_simt
     src = build_simt.device_part(os.path.join(build_simt.CSRC, "deposit_sorted.cu"))
-    barrier = "if (c0 != pbeg) __syncthreads();"
+    barrier = "__syncthreads();   // every particle of the chunk is in the tile"
     assert src.count(barrier) == 1
     lib = load(build_simt.compile_kernels(src.replace(barrier, "(void)0;"), str(tmp_path)))
     rng = np.random.default_rng(3)
