@@ -1,5 +1,6 @@
 // extern "C" surface of libastrild_pk.so (declared in include/astrild_pk.h).
 #include "apk_common.cuh"
+#include <cstdlib>
 #include "deposit_common.cuh"
 #include <cmath>
 #include <cstring>
@@ -426,6 +427,7 @@ int apk_binning_create(apk_binning **out, apk_plan *P, int n_a, int n_b, int nz,
     B->wz = df;
     if (has_comp) { B->icomp2_a = df + nz; B->icomp2_b = B->icomp2_a + n_a; B->icomp2_z = B->icomp2_b + n_b; }
 
+    if (const char *v = getenv("APK_BIN_TABLE")) B->use_table = v[0] == '1' && nedges < 65534;      // experimental
     B->partial_ctas = P->num_sms * 3;   // = resident CTAs (80 regs, 51 KB smem)
     const size_t pbytes = sizeof(double) * 4 * (size_t)B->partial_ctas * (nedges + 1);
     if (cudaMalloc(&B->partial, pbytes) != cudaSuccess) {
@@ -440,6 +442,8 @@ int apk_binning_destroy(apk_binning *B) {
     DeviceGuard guard(B->plan->device);
     if (B->tables) cudaFree(B->tables);
     if (B->partial) cudaFree(B->partial);
+    if (B->bins) cudaFree(B->bins);
+    if (B->geo) cudaFree(B->geo);
     if (B->ev_ready) for (auto &e : B->ev) cudaEventDestroy(e);
     delete B;
     return 0;

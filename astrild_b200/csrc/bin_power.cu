@@ -39,7 +39,11 @@ struct BinArgs {
     float kmin_f, inv_dk_f;
     double *part_k, *part_p, *part_pim;   // [ctas][nedges+1]
     unsigned long long *part_n;           // [ctas][nedges+1]
+    unsigned short *bins;                 // [n_a][n_b][nz] shell of every mode (MODE 1 writes it, MODE 2 reads it)
 };
+
+// shells are < 65534; the two largest codes mark modes outside the edges
+constexpr unsigned short BIN_UNDER = 0xfffe, BIN_OVER = 0xffff;
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -56,7 +60,11 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *addr, unsigned l
 template <bool INTERLACED, bool CROSS>
 struct BinRows { static constexpr int TA = (INTERLACED || CROSS) ? 2 : 4; };
 
-template <bool INTERLACED, bool CROSS, bool COMP>
+// MODE 0: everything in one pass (the default).  Experimental split (APK_BIN_TABLE=1): the shell of a mode, the mode
+// counts and sum(w k) depend on the binning alone, so MODE 1 computes them once per binning object -- same float64
+// digitize, no grid read -- and stores the shell of every mode as uint16; MODE 2, run per spectrum, reads that
+// table instead of doing any float64 wavenumber arithmetic and only accumulates sum(w P).
+template <bool INTERLACED, bool CROSS, bool COMP, int MODE = 0>
 __global__ void __launch_bounds__(BIN_THREADS, 3)
 bin_power_kernel(BinArgs A) {
     constexpr int BIN_TA = BinRows<INTERLACED, CROSS>::TA;
@@ -130,6 +138,7 @@ bin_power_kernel(BinArgs A) {
 #pragma unroll
         for (int t = 0; t < BIN_TA; ++t) dc_row[t] = iz == 0 && ia0 + t == A.dc_a;
         float2 v1[BIN_TA], v1s[BIN_TA], v2[BIN_TA], v2s[BIN_TA];
+        unsigned short vb[BIN_TA];               // MODE 2: the stored shells of the prefetched row
         double n_kb2 = 0.0;                      // b-row tables travel with the prefetched row
         float n_icb = 1.f;
         float2 n_phb = make_float2(1.f, 0.f);
@@ -147,6 +156,8 @@ bin_power_kernel(BinArgs A) {
             for (int t = 0; t < BIN_TA; ++t) {
                 if ((ka2[t] + n_kb2) + kz2_min >= e2_last) continue;      // warp-uniform
                 const size_t idx = base[t] + (size_t)ib * A.nz;
+                if (MODE == 2) vb[t] = A.bins[idx];
+                if (MODE == 1) continue;
                 v1[t] = __ldcs(A.c1 + idx);
                 if (INTERLACED) v1s[t] = __ldcs(A.c1s + idx);
                 if (CROSS) {
@@ -159,8 +170,10 @@ bin_power_kernel(BinArgs A) {
         if (ib0 < ib1) load_row(ib0);
         for (int ib = ib0; ib < ib1; ++ib) {
             float2 c1[BIN_TA], c1s[BIN_TA], c2[BIN_TA], c2s[BIN_TA];
+            unsigned short cb[BIN_TA];
 #pragma unroll
             for (int t = 0; t < BIN_TA; ++t) {
+                cb[t] = vb[t];
                 c1[t] = v1[t];
                 if (INTERLACED) c1s[t] = v1s[t];
                 if (CROSS) { c2[t] = v2[t]; if (INTERLACED) c2s[t] = v2s[t]; }
@@ -173,67 +186,80 @@ bin_power_kernel(BinArgs A) {
 #pragma unroll
             for (int t = 0; t < BIN_TA; ++t) {
                 if (!(zvalid && avalid[t])) continue;
-                const double k2 = (ka2[t] + kb2) + kz2;
                 const unsigned int wi = singular ? 1u : 2u;
-                if (k2 >= e2_last) { over_cnt += wi; continue; }
-                if (k2 < e2_first) { under_cnt += wi; continue; }
-                // --- bin: float guess, exact float64 fix-up against kedges^2 -----------------
-                // sqrt(k2): float rsqrt seed + one Newton step in float64 (rel. error ~1e-14)
-                const float k2f = (float)k2;
-                const float rs = k2f > 0.f ? rsqrtf(k2f) : 0.f;
-                const double y = (double)rs;
-                double kk = k2 * y;
-                kk = fma(0.5 * y, fma(-kk, kk, k2), kk);
-                int bin = (int)((k2f * rs - A.kmin_f) * A.inv_dk_f) + 1;
-                bin = max(1, min(bin, nedges - 1));
-                while (k2 < s_e2[bin - 1]) --bin;
-                while (k2 >= s_e2[bin]) ++bin;
-                // --- power of this mode --------------------------------------------------------
-                float2 a = c1[t];
-                if (INTERLACED) {
-                    const float2 ph = cmul(pha[t], phb);
-                    const float2 s = cmul(c1s[t], ph);
-                    a = make_float2(0.5f * (a.x + s.x), 0.5f * (a.y + s.y));
+                int bin;
+                double kk = 0.0;
+                if (MODE == 2) {
+                    // lines beyond the last edge were skipped by load_row (cb is stale there): same test here
+                    if ((ka2[t] + kb2) + kz2_min >= e2_last) continue;
+                    if (cb[t] >= BIN_UNDER) continue;
+                    bin = cb[t];
+                } else {
+                    const double k2 = (ka2[t] + kb2) + kz2;
+                    const size_t idx = base[t] + (size_t)ib * A.nz;
+                    if (k2 >= e2_last) { over_cnt += wi; if (MODE == 1 && (ka2[t] + kb2) + kz2_min < e2_last) A.bins[idx] = BIN_OVER; continue; }
+                    if (k2 < e2_first) { under_cnt += wi; if (MODE == 1) A.bins[idx] = BIN_UNDER; continue; }
+                    // --- bin: float guess, exact float64 fix-up against kedges^2 -----------------
+                    // sqrt(k2): float rsqrt seed + one Newton step in float64 (rel. error ~1e-14)
+                    const float k2f = (float)k2;
+                    const float rs = k2f > 0.f ? rsqrtf(k2f) : 0.f;
+                    const double y = (double)rs;
+                    kk = k2 * y;
+                    kk = fma(0.5 * y, fma(-kk, kk, k2), kk);
+                    bin = (int)((k2f * rs - A.kmin_f) * A.inv_dk_f) + 1;
+                    bin = max(1, min(bin, nedges - 1));
+                    while (k2 < s_e2[bin - 1]) --bin;
+                    while (k2 >= s_e2[bin]) ++bin;
+                    if (MODE == 1) A.bins[idx] = (unsigned short)bin;
                 }
-                float pre, pim;
-                if (CROSS) {
-                    float2 b = c2[t];
+                // --- power of this mode --------------------------------------------------------
+                float pre = 0.f, pim = 0.f;
+                if (MODE != 1) {
+                    float2 a = c1[t];
                     if (INTERLACED) {
                         const float2 ph = cmul(pha[t], phb);
-                        const float2 s = cmul(c2s[t], ph);
-                        b = make_float2(0.5f * (b.x + s.x), 0.5f * (b.y + s.y));
+                        const float2 s = cmul(c1s[t], ph);
+                        a = make_float2(0.5f * (a.x + s.x), 0.5f * (a.y + s.y));
                     }
-                    pre = a.x * b.x + a.y * b.y;
-                    pim = a.y * b.x - a.x * b.y;
-                } else {
-                    pre = a.x * a.x + a.y * a.y;
-                    pim = 0.f;
+                    if (CROSS) {
+                        float2 b = c2[t];
+                        if (INTERLACED) {
+                            const float2 ph = cmul(pha[t], phb);
+                            const float2 s = cmul(c2s[t], ph);
+                            b = make_float2(0.5f * (b.x + s.x), 0.5f * (b.y + s.y));
+                        }
+                        pre = a.x * b.x + a.y * b.y;
+                        pim = a.y * b.x - a.x * b.y;
+                    } else {
+                        pre = a.x * a.x + a.y * a.y;
+                        pim = 0.f;
+                    }
+                    if (COMP) { const float ic = ica[t] * icb; pre *= ic; pim *= ic; }
+                    if (dc_row[t] && ib == A.dc_b) { pre = 0.f; pim = 0.f; }
                 }
-                if (COMP) { const float ic = ica[t] * icb; pre *= ic; pim *= ic; }
-                if (dc_row[t] && ib == A.dc_b) { pre = 0.f; pim = 0.f; }
                 const double w = (double)wi;
-                if (CROSS && singular && pim != 0.f) red_add_f64(g_pim + bin, (double)pim);
+                if (MODE != 1 && CROSS && singular && pim != 0.f) red_add_f64(g_pim + bin, (double)pim);
                 // --- private window update ---------------------------------------------------
                 const int slot = (bin & (BIN_W - 1)) * BIN_THREADS + tid;
                 int2 m = s_meta[slot];
                 double ps, ks;
                 if (m.x != bin) {
                     if (m.x >= 0) {
-                        red_add_f64(g_p + m.x, s_ps[slot]);
-                        red_add_f64(g_k + m.x, s_ks[slot]);
-                        red_add_u64(g_n + m.x, (unsigned long long)m.y);
+                        if (MODE != 1) red_add_f64(g_p + m.x, s_ps[slot]);
+                        if (MODE != 2) red_add_f64(g_k + m.x, s_ks[slot]);
+                        if (MODE != 2) red_add_u64(g_n + m.x, (unsigned long long)m.y);
                     }
                     m = make_int2(bin, 0);
                     ps = 0.0;
                     ks = 0.0;
                 } else {
-                    ps = s_ps[slot];
-                    ks = s_ks[slot];
+                    ps = MODE != 1 ? s_ps[slot] : 0.0;
+                    ks = MODE != 2 ? s_ks[slot] : 0.0;
                 }
                 m.y += (int)wi;
                 s_meta[slot] = m;
-                s_ps[slot] = fma(w, (double)pre, ps);
-                s_ks[slot] = fma(w, kk, ks);
+                if (MODE != 1) s_ps[slot] = fma(w, (double)pre, ps);
+                if (MODE != 2) s_ks[slot] = fma(w, kk, ks);
             }
         }
     }
@@ -244,11 +270,12 @@ bin_power_kernel(BinArgs A) {
         const int slot = s * BIN_THREADS + tid;
         const int2 m = s_meta[slot];
         if (m.x >= 0) {
-            red_add_f64(g_p + m.x, s_ps[slot]);
-            red_add_f64(g_k + m.x, s_ks[slot]);
-            red_add_u64(g_n + m.x, (unsigned long long)m.y);
+            if (MODE != 1) red_add_f64(g_p + m.x, s_ps[slot]);
+            if (MODE != 2) red_add_f64(g_k + m.x, s_ks[slot]);
+            if (MODE != 2) red_add_u64(g_n + m.x, (unsigned long long)m.y);
         }
     }
+    if (MODE == 2) return;
     // under/overflow counts: warp-reduce, one RED per warp
     for (int o = 16; o > 0; o >>= 1) {
         under_cnt += __shfl_xor_sync(0xffffffffu, under_cnt, o);
@@ -296,13 +323,23 @@ size_t bin_smem_bytes(int nedges) {
     return sizeof(double) * (e_pad + 2 * BIN_W * BIN_THREADS) + sizeof(int2) * BIN_W * BIN_THREADS;
 }
 
-template <bool I, bool C, bool P>
+template <bool I, bool C, bool P, int MODE>
 static int launch_bin(const BinArgs &A, int ctas, size_t smem, cudaStream_t st) {
-    auto kern = bin_power_kernel<I, C, P>;
+    auto kern = bin_power_kernel<I, C, P, MODE>;
     APK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, BIN_THREADS, smem, st>>>(A);
     APK_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int MODE>
+static int launch_bin_variant(bool interlaced, bool cross, bool comp, const BinArgs &A, int ctas, size_t smem, cudaStream_t st) {
+    if (interlaced) {
+        if (cross) return comp ? launch_bin<true, true, true, MODE>(A, ctas, smem, st) : launch_bin<true, true, false, MODE>(A, ctas, smem, st);
+        return comp ? launch_bin<true, false, true, MODE>(A, ctas, smem, st) : launch_bin<true, false, false, MODE>(A, ctas, smem, st);
+    }
+    if (cross) return comp ? launch_bin<false, true, true, MODE>(A, ctas, smem, st) : launch_bin<false, true, false, MODE>(A, ctas, smem, st);
+    return comp ? launch_bin<false, false, true, MODE>(A, ctas, smem, st) : launch_bin<false, false, false, MODE>(A, ctas, smem, st);
 }
 
 int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void *c2,
@@ -320,6 +357,7 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
     A.n_a = B->n_a; A.n_b = B->n_b; A.nz = B->nz; A.nedges = B->nedges;
     A.dc_a = B->dc_a; A.dc_b = B->dc_b;
     A.kmin_f = (float)B->kmin_guess; A.inv_dk_f = (float)B->inv_dk_guess;
+    A.bins = B->bins;
 
     const int ctas = B->partial_ctas;
     const int nb1 = B->nedges + 1;
@@ -336,29 +374,51 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
     A.part_p = A.part_k + (size_t)ctas * nb1;
     A.part_pim = A.part_p + (size_t)ctas * nb1;
     A.part_n = (unsigned long long *)(A.part_pim + (size_t)ctas * nb1);
-    APK_CUDA(cudaMemsetAsync(B->partial, 0, sizeof(double) * 4 * (size_t)ctas * nb1, st));
-
+    const size_t pbytes = sizeof(double) * 4 * (size_t)ctas * nb1;
     const size_t smem = bin_smem_bytes(B->nedges);
     const bool comp = B->has_comp;
+
+    // experimental (APK_BIN_TABLE=1): geometry once per binning object, then table-driven data passes
+    const bool tabled = B->use_table;
+    if (tabled && !B->bins) {
+        const size_t modes = (size_t)B->n_a * B->n_b * B->nz;
+        APK_CUDA(cudaMalloc(&B->bins, modes * sizeof(unsigned short)));
+        APK_CUDA(cudaMalloc(&B->geo, sizeof(double) * 4 * (size_t)nb1));
+        A.bins = B->bins;
+        APK_CUDA(cudaMemsetAsync(B->partial, 0, pbytes, st));
+        // the geometry does not depend on which grids are given: one (auto, single grid) work distribution
+        BinArgs Ag = A;
+        Ag.c1s = Ag.c2 = Ag.c2s = nullptr;
+        Ag.n_ga = (B->n_a + 3) / 4;
+        int sg = B->n_b;
+        while (sg > 32 && (long long)Ag.n_ga * A.n_zc * ((B->n_b + sg - 1) / sg) < 4 * warps) sg >>= 1;
+        Ag.seg_b = sg;
+        Ag.n_sb = (B->n_b + sg - 1) / sg;
+        if (int rc = launch_bin<false, false, false, 1>(Ag, ctas, smem, st)) return rc;
+        double *g = B->geo;
+        bin_fold_kernel<<<(nb1 + 3) / 4, 128, 0, st>>>(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1,
+                                                          g, g + nb1, g + 2 * nb1, (long long *)(g + 3 * nb1));
+        APK_CUDA(cudaGetLastError());
+    }
+
+    APK_CUDA(cudaMemsetAsync(B->partial, 0, pbytes, st));
     const bool timing = B->plan->timing;
     if (timing && !B->ev_ready) {
         for (auto &e : B->ev) APK_CUDA(cudaEventCreate(&e));
         B->ev_ready = true;
     }
     if (timing) APK_CUDA(cudaEventRecord(B->ev[0], st));
-    int rc;
-    if (interlaced) {
-        if (cross) rc = comp ? launch_bin<true, true, true>(A, ctas, smem, st) : launch_bin<true, true, false>(A, ctas, smem, st);
-        else rc = comp ? launch_bin<true, false, true>(A, ctas, smem, st) : launch_bin<true, false, false>(A, ctas, smem, st);
-    } else {
-        if (cross) rc = comp ? launch_bin<false, true, true>(A, ctas, smem, st) : launch_bin<false, true, false>(A, ctas, smem, st);
-        else rc = comp ? launch_bin<false, false, true>(A, ctas, smem, st) : launch_bin<false, false, false>(A, ctas, smem, st);
-    }
+    int rc = tabled ? launch_bin_variant<2>(interlaced, cross, comp, A, ctas, smem, st)
+                    : launch_bin_variant<0>(interlaced, cross, comp, A, ctas, smem, st);
     if (rc) return rc;
     if (timing) APK_CUDA(cudaEventRecord(B->ev[1], st));
     bin_fold_kernel<<<(nb1 + 3) / 4, 128, 0, st>>>(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1,
                                                       ksum, psum_re, psum_im, (long long *)nmodes);
     APK_CUDA(cudaGetLastError());
+    if (tabled) {        // mode counts and sum(w k) come from the geometry pass
+        APK_CUDA(cudaMemcpyAsync(ksum, B->geo, sizeof(double) * nb1, cudaMemcpyDeviceToDevice, st));
+        APK_CUDA(cudaMemcpyAsync(nmodes, B->geo + 3 * (size_t)nb1, sizeof(long long) * nb1, cudaMemcpyDeviceToDevice, st));
+    }
     if (timing) APK_CUDA(cudaEventRecord(B->ev[2], st));
     B->timed = timing;
     return 0;

@@ -11,9 +11,19 @@
 using namespace apk;
 
 namespace {
-template <bool I, bool C, bool P>
+template <bool I, bool C, bool P, int MODE>
 void go(const BinArgs &A, int ctas) {
-    simt::launch(ctas, BIN_THREADS, [&] { bin_power_kernel<I, C, P>(A); });
+    simt::launch(ctas, BIN_THREADS, [&] { bin_power_kernel<I, C, P, MODE>(A); });
+}
+template <int MODE>
+void go_variant(bool interlaced, bool cross, bool comp, const BinArgs &A, int ctas) {
+    if (interlaced) {
+        if (cross) comp ? go<true, true, true, MODE>(A, ctas) : go<true, true, false, MODE>(A, ctas);
+        else comp ? go<true, false, true, MODE>(A, ctas) : go<true, false, false, MODE>(A, ctas);
+    } else {
+        if (cross) comp ? go<false, true, true, MODE>(A, ctas) : go<false, true, false, MODE>(A, ctas);
+        else comp ? go<false, false, true, MODE>(A, ctas) : go<false, false, false, MODE>(A, ctas);
+    }
 }
 }  // namespace
 
@@ -55,26 +65,49 @@ extern "C" int simt_bin_power(const void *c1, const void *c1s, const void *c2, c
     const int ta = (interlaced || cross) ? 2 : 4;
     A.n_ga = (n_a + ta - 1) / ta;
     A.n_zc = (nz + 31) / 32;
-    const long long warps = (long long)ctas * (BIN_THREADS / 32);
+    const long long warps = (long long)(ctas & 0xffff) * (BIN_THREADS / 32);
     int seg = n_b;
     while (seg > 32 && (long long)A.n_ga * A.n_zc * ((n_b + seg - 1) / seg) < 4 * warps) seg >>= 1;
     A.seg_b = seg;
     A.n_sb = (n_b + seg - 1) / seg;
-    std::vector<double> partial(4 * (size_t)ctas * nb1, 0.0);
+    const int nct = ctas & 0xffff;
+    std::vector<double> partial(4 * (size_t)nct * nb1, 0.0);
     A.part_k = partial.data();
-    A.part_p = A.part_k + (size_t)ctas * nb1;
-    A.part_pim = A.part_p + (size_t)ctas * nb1;
-    A.part_n = (unsigned long long *)(A.part_pim + (size_t)ctas * nb1);
+    A.part_p = A.part_k + (size_t)nct * nb1;
+    A.part_pim = A.part_p + (size_t)nct * nb1;
+    A.part_n = (unsigned long long *)(A.part_pim + (size_t)nct * nb1);
     const bool comp = has_comp;
-    if (interlaced) {
-        if (cross) comp ? go<true, true, true>(A, ctas) : go<true, true, false>(A, ctas);
-        else comp ? go<true, false, true>(A, ctas) : go<true, false, false>(A, ctas);
+    const bool tabled = (ctas >> 16) != 0;       // high half of `ctas`: experimental table-driven variant
+    ctas &= 0xffff;
+    std::vector<unsigned short> bins;
+    std::vector<double> geo(4 * (size_t)nb1, 0.0);
+    if (tabled) {
+        bins.assign((size_t)n_a * n_b * nz, 0x1234);
+        A.bins = bins.data();
+        BinArgs Ag = A;
+        Ag.c1s = Ag.c2 = Ag.c2s = nullptr;
+        Ag.n_ga = (n_a + 3) / 4;
+        int sg = n_b;
+        while (sg > 32 && (long long)Ag.n_ga * A.n_zc * ((n_b + sg - 1) / sg) < 4 * warps) sg >>= 1;
+        Ag.seg_b = sg;
+        Ag.n_sb = (n_b + sg - 1) / sg;
+        go<false, false, false, 1>(Ag, ctas);
+        simt::launch((nb1 + 3) / 4, 128, [&] {
+            bin_fold_kernel(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1, geo.data(), geo.data() + nb1,
+                            geo.data() + 2 * nb1, (long long *)(geo.data() + 3 * nb1));
+        });
+        std::fill(partial.begin(), partial.end(), 0.0);
+        go_variant<2>(interlaced, cross, comp, A, ctas);
     } else {
-        if (cross) comp ? go<false, true, true>(A, ctas) : go<false, true, false>(A, ctas);
-        else comp ? go<false, false, true>(A, ctas) : go<false, false, false>(A, ctas);
+        A.bins = nullptr;
+        go_variant<0>(interlaced, cross, comp, A, ctas);
     }
     simt::launch((nb1 + 3) / 4, 128, [&] {
         bin_fold_kernel(A.part_k, A.part_p, A.part_pim, A.part_n, ctas, nb1, ksum, psum_re, psum_im, nmodes);
     });
+    if (tabled) {
+        std::memcpy(ksum, geo.data(), sizeof(double) * nb1);
+        std::memcpy(nmodes, geo.data() + 3 * (size_t)nb1, sizeof(long long) * nb1);
+    }
     return 0;
 }

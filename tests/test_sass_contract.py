@@ -64,7 +64,7 @@ def test_partition_counts_with_reds_and_scatters_with_returning_atomics(sass):
 
 
 def test_binning_kernel_evicts_with_float64_reds(sass):
-    ops = one(sass, r"bin_power_kernelILb1ELb0ELb1")             # interlaced auto spectrum, compensated
+    ops = one(sass, r"bin_power_kernelILb1ELb0ELb1ELi0")        # interlaced auto spectrum, compensated, one-pass mode
     assert sum(op.startswith("RED") and "F64" in op for op in ops) >= 4
     assert count(ops, "ATOMG") == 0 and not any(op.startswith("ATOMS") for op in ops)
     assert count(ops, "LDL") + count(ops, "STL") == 0
