@@ -188,8 +188,12 @@ static int deposit_impl(apk_plan *P, const void *p0, const void *p1, const void 
         APK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, st));
         if (mesh1) APK_CUDA(cudaMemsetAsync(mesh1, 0, mesh_bytes, st));
     }
-    if (method == APK_DEPOSIT_AUTO)
-        method = (np >= (1 << 18)) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
+    if (method == APK_DEPOSIT_AUTO) {
+        // the sorted path pays per brick (a tile to clear and to flush): it wins once the bricks are populated --
+        // more than ~16 particles per brick of ~2200 cells -- and the set is large enough to amortise its launches
+        const double bricks = (double)G.nplanes * P->N * P->N / 2160.0;
+        method = (np >= (1 << 18) && (double)np >= 16.0 * bricks) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
+    }
     if (P->timing) P->dep_timed = false;            // an untimed call leaves the last timed deposit's events alone
     if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
         return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);

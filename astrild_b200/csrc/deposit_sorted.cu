@@ -741,18 +741,29 @@ brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict
 // memory as 32-bit FIXED-POINT integers and every one of the S^3 weights goes there with a native integer ATOMS.ADD
 // (shared-memory float atomics are CAS loops on sm_100; integer adds are not).  No in-brick sort, no per-cell loop:
 // all 32 lanes work on every instruction, whatever the cell occupancy.
-//   quantum 2^-PP_FRAC_BITS of a particle's mass; a weight is rounded to it by ONE FFMA against a magic constant
-//   (1.5 * 2^(23 - PP_FRAC_BITS): the sum lands in a binade whose ulp is the quantum, so the low mantissa bits ARE the
-//   fixed-point value); at most PP_FLUSH particles are accumulated between two flushes, so that a cell cannot
-//   overflow 32 bits even if every one of them sits in it.  Integer adds commute: a brick's contribution to the mesh
-//   does not depend on the order in which the partition filed its particles.
+//   Quantum 2^-s of a particle's mass, s chosen PER CHUNK of <= PP_FLUSH particles as large as 32 bits allow if every
+//   particle of the chunk put its largest possible weight (1 for CIC, 0.75^3 for TSC) into one cell: s = 22 for the
+//   ~2200 particles of a brick at one particle per cell (TSC), 20..21 for a full chunk, 22 / 23 for sparse bricks.
+//   A weight is rounded to the quantum by ONE FFMA against a magic constant (1.5 * 2^(23 - s): the sum lands in a
+//   binade whose ulp is the quantum, so the low mantissa bits ARE the fixed-point value).  Integer adds commute: a
+//   brick's contribution to the mesh does not depend on the order in which the partition filed its particles.
 //   The tile goes to the mesh as before: one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
-constexpr int PP_FRAC_BITS = 20;
-constexpr int PP_FLUSH = 4095;                        // particles between two flushes: 4095 * 2^20 < 2^32
+constexpr int PP_FLUSH = 4095;                        // particles between two flushes
 constexpr int PP_THREADS = 256;
 #ifndef APK_PP_CTAS
 #define APK_PP_CTAS 6
 #endif
+
+// fractional bits for a chunk of n particles: n * wmax * 2^s < 2^32, s <= SMAX (the magic-constant trick needs
+// wmax <= 2^(22 - s))
+template <int S>
+__device__ __forceinline__ int pp_frac_bits(int n) {
+    constexpr float WMAX = (S == 3) ? 0.43f : 1.001f;          // 0.75^3 = 0.4219 / 1, padded for the rounding
+    constexpr int SMAX = (S == 3) ? 23 : 22;
+    const float room = (4294967296.f / WMAX) / (float)n;
+    const int s = ((__float_as_int(room) >> 23) & 0xff) - 127;  // floor(log2(room))
+    return min(s, SMAX);
+}
 
 template <int S> struct PPTile {
     static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
@@ -780,9 +791,6 @@ brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restr
     __shared__ unsigned int tile[T::CELLS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int nfilled = *nfilled_ptr;
-    const float magic = 1.5f * (float)(1 << (23 - PP_FRAC_BITS));
-    const unsigned int magic_bits = (unsigned int)__float_as_int(magic);
-    const float quantum = 1.f / (float)(1 << PP_FRAC_BITS);
 
     for (unsigned int slot = blockIdx.x; slot < nfilled; slot += gridDim.x) {
         const unsigned int brick = filled[slot];
@@ -796,6 +804,10 @@ brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restr
 
         for (unsigned int c0 = pbeg; c0 < pend; c0 += PP_FLUSH) {
             const unsigned int c1 = min(c0 + (unsigned int)PP_FLUSH, pend);
+            const int frac_bits = pp_frac_bits<S>((int)(c1 - c0));
+            const unsigned int magic_bits = ((unsigned int)(127 + 23 - frac_bits) << 23) | 0x400000u;   // 1.5 * 2^(23 - s)
+            const float magic = __int_as_float((int)magic_bits);
+            const float quantum = __int_as_float((127 - frac_bits) << 23);                                // 2^-s
             // ---- one thread per particle; the next particle's loads are in flight while this one is deposited ----
             unsigned int p = c0 + tid;
             VT nxt = {};

@@ -177,15 +177,21 @@ class PkEngine:
         slab = self.n0 < self.N
         if out is None:
             out = self.new_mesh(ghosts=slab)
+        scalar = float(mass) if (mass is not None and np.isscalar(mass)) else 1.0
+        # a scalar weight multiplies what THIS call deposits: when accumulating into a mesh that already holds
+        # something, deposit into a scratch mesh first (scaling `out` would rescale its previous content)
+        target = out if (zero or scalar == 1.0) else torch.empty_like(out)
         self.ensure_workspace(npart, m is not None)
         _lib.call("apk_deposit", self._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout,
                   _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64,
                   float(1.0 / self.L if pos_scale is None else pos_scale), _ptr(m),
                   _lib.APK_F32 if (m is None or m.dtype == torch.float32) else _lib.APK_F64,
-                  int(npart), rs, float(shift), _lib.DEPOSIT_METHODS[method], int(bool(zero)),
-                  _ptr(out), self.stream)
-        if mass is not None and np.isscalar(mass) and float(mass) != 1.0:
-            out.mul_(float(mass))
+                  int(npart), rs, float(shift), _lib.DEPOSIT_METHODS[method], int(bool(zero) or target is not out),
+                  _ptr(target), self.stream)
+        if target is not out:
+            out.add_(target, alpha=scalar)
+        elif scalar != 1.0:
+            out.mul_(scalar)
         del keep
         return out
 
@@ -203,16 +209,32 @@ class PkEngine:
                 raise AstrildPkError("mass must be a scalar or have one entry per particle")
         slab = self.n0 < self.N
         m0, m1 = out if out is not None else (self.new_mesh(ghosts=slab), self.new_mesh(ghosts=slab))
+        scalar = float(mass) if (mass is not None and np.isscalar(mass)) else 1.0
+        scratch = not zero and scalar != 1.0          # see deposit(): never rescale what the meshes already hold
+        t0, t1 = (torch.empty_like(m0), torch.empty_like(m1)) if scratch else (m0, m1)
         self.ensure_workspace(npart, m is not None, True)
         _lib.call("apk_deposit_interlaced", self._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout,
                   _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64,
                   float(1.0 / self.L if pos_scale is None else pos_scale), _ptr(m),
                   _lib.APK_F32 if (m is None or m.dtype == torch.float32) else _lib.APK_F64,
-                  int(npart), rs, _lib.DEPOSIT_METHODS[method], int(bool(zero)), _ptr(m0), _ptr(m1), self.stream)
-        if mass is not None and np.isscalar(mass) and float(mass) != 1.0:
-            m0.mul_(float(mass)); m1.mul_(float(mass))
+                  int(npart), rs, _lib.DEPOSIT_METHODS[method], int(bool(zero) or scratch), _ptr(t0), _ptr(t1), self.stream)
+        if scratch:
+            m0.add_(t0, alpha=scalar); m1.add_(t1, alpha=scalar)
+        elif scalar != 1.0:
+            m0.mul_(scalar); m1.mul_(scalar)
         del keep
         return m0, m1
+
+    def pow2_scaled(self, mass) -> tuple:
+        """(mass / 2^e, 2^e) with 2^e the power of two nearest to max |mass| (exact scaling).  Masses in physical
+        units (1e10..1e15) would put |field(k)|^2 near the float32 range in the binning kernel; the factor is
+        folded back into the host-side scale, or cancels when the field is divided by its mean."""
+        m = self._to_device(mass)
+        top = float(m.abs().max().item()) if m.numel() else 1.0
+        if not np.isfinite(top) or top <= 0.0:
+            return m, 1.0
+        fac = 2.0 ** round(float(np.log2(top)))
+        return (m * (1.0 / fac)).contiguous(), fac
 
     def _deposit_shifts(self, pos, mass, resampler, shifts, pos_scale, method, meshes, zero):
         if tuple(shifts) == (0.0, 0.5):
@@ -249,11 +271,18 @@ class PkEngine:
 
         hcols = [as_host_tensor(c) for c in cols] if cols is not None else [as_host_tensor(pos)]
         hmass = None if (mass is None or np.isscalar(mass)) else as_host_tensor(mass)
+        scalar = float(mass) if (mass is not None and np.isscalar(mass)) else 1.0
         srcs = hcols + ([hmass] if hmass is not None else [])
         cur = torch.cuda.current_stream(self.device)
         copy_stream = torch.cuda.Stream(self.device)
         bufs = [[torch.empty((chunk_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in srcs]
                 for _ in range(2)]
+        # the allocator may hand out blocks whose last use is still queued on `cur`: order the first copy after it,
+        # and tell the allocator that the copy stream uses these blocks
+        copy_stream.wait_stream(cur)
+        for pair in bufs:
+            for buf in pair:
+                buf.record_stream(copy_stream)
         ready = [torch.cuda.Event() for _ in range(2)]
         free = [None, None]
         self.ensure_workspace(chunk_rows, hmass is not None, len(shifts) == 2)
@@ -269,11 +298,14 @@ class PkEngine:
             cur.wait_event(ready[s])
             part = [buf[: b - a] for buf in bufs[s]]
             ppos = tuple(part[:3]) if cols is not None else part[0]
-            pm = part[-1] if hmass is not None else mass
+            pm = part[-1] if hmass is not None else None         # a scalar weight is applied once, after the loop
             self._deposit_shifts(ppos, pm, resampler, shifts, pos_scale, method, meshes, c == 0)
             free[s] = torch.cuda.Event()
             free[s].record(cur)
         cur.wait_stream(copy_stream)
+        if scalar != 1.0:
+            for mesh in meshes:
+                mesh.mul_(scalar)
         return meshes
 
     # ------------------------------------------------------------------ stage 1': ArrayMesh

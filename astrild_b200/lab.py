@@ -147,17 +147,53 @@ class CatalogMesh:
         self._normalize, self._pos_scale, self._method = bool(normalize), pos_scale, method
         if compensated and str(resampler).lower() not in ("cic", "tsc"):
             raise AstrildPkError("compensated=True needs resampler 'cic' or 'tsc'")
+        self.shotnoise = 0.0
+
+    def _npart(self) -> int:
+        p = self._pos
+        first = p[0] if (isinstance(p, (tuple, list)) and len(p) == 3 and not np.isscalar(p[0])) else p
+        return int(first.shape[0])
+
+    def _shotnoise(self) -> float:
+        """V * W2 / W^2 with W = sum of weights, W2 = sum of squared weights, float64 sums (nbodykit
+        CatalogMesh.to_real_field attrs; V / N for unit weights)."""
+        V, n, w = float(self.attrs["BoxSize"][0]) ** 3, self._npart(), self._w
+        if n == 0:
+            return 0.0
+        if w is None or np.isscalar(w):
+            m = 1.0 if w is None else float(w)
+            return V / n if self._normalize else n * m * m / V
+        if isinstance(w, torch.Tensor):
+            wd = w.double()
+            W, W2 = float(wd.sum().item()), float((wd * wd).sum().item())
+        else:
+            wd = np.asarray(w, dtype=np.float64)
+            W, W2 = float(wd.sum()), float((wd * wd).sum())
+        if not self._normalize:
+            return W2 / V                              # the un-normalised field rho = mass / dx^3: rho_mean^2 times the above
+        return V * W2 / (W * W) if W != 0.0 else 0.0
 
     def _complex_fields(self):
         eng, a = self._eng, self.attrs
         shifts = (0.0, 0.5) if a["interlaced"] else (0.0,)
-        meshes = eng.deposit_many(self._pos, self._w, a["resampler"], shifts, self._pos_scale, self._method)
+        w, unit = self._w, 1.0
+        if w is not None and not np.isscalar(w) and isinstance(w, torch.Tensor) and w.is_cuda:
+            w, unit = eng.pow2_scaled(w)              # device weights: deposit in units of 2^e (exact), see pow2_scaled
+        elif w is not None and not np.isscalar(w):
+            wa = np.asarray(w)
+            top = float(np.abs(wa).max()) if wa.size else 1.0
+            if np.isfinite(top) and top > 0.0:
+                unit = 2.0 ** round(float(np.log2(top)))
+                w = wa * wa.dtype.type(1.0 / unit) if wa.dtype in (np.float32, np.float64) else wa.astype(np.float64) / unit
+        meshes = eng.deposit_many(self._pos, w, a["resampler"], shifts, self._pos_scale, self._method)
         mesh, mesh_s = meshes[0], (meshes[1] if a["interlaced"] else None)
         total = eng.mesh_sum(mesh) if self._normalize else None
         if self._normalize:
-            scale = eng.N ** 3 / total
+            scale = eng.N ** 3 / total                # 1 + delta = mesh / mean: the unit cancels
         else:
-            scale = 1.0 / (eng.L / eng.N) ** 3
+            scale = unit / (eng.L / eng.N) ** 3
+        # nbodykit CatalogMesh attrs (SURVEY.md A.3): shotnoise = V * sum(w^2) / sum(w)^2  (= V / N unweighted)
+        self.shotnoise = self._shotnoise()
         c = eng.r2c(mesh)
         cs = eng.r2c(mesh_s) if mesh_s is not None else None
         comp = (str(a["resampler"]).lower(), a["interlaced"]) if a["compensated"] else None
@@ -190,8 +226,8 @@ class FFTPower:
 
     Result in ``self.power`` with variables ``k`` (mean |k| of the modes in the bin, NaN if
     empty), ``power`` (complex; real part is P(k)), ``modes`` (int64) and attrs including
-    ``shotnoise`` (0 for ArrayMesh input, V*sum(w^2)/sum(w)^2 is NOT computed here: astrild
-    only ever feeds ArrayMesh).
+    ``shotnoise``: 0 for ArrayMesh input (astrild's case) and for cross
+    spectra, V*sum(w^2)/sum(w)^2 for the auto spectrum of a CatalogMesh (nbodykit semantics).
     """
 
     def __init__(self, first, mode="1d", Nmesh=None, BoxSize=None, second=None, los=(0, 0, 1),
@@ -219,10 +255,14 @@ class FFTPower:
         scale = L ** 3 * s1 * s2 / float(N) ** 6
         res = eng.bin_power(binning, c1, c1s, c2, c2s, scale)
         edges = binning.edges
+        # nbodykit FFTBase._compute_3d_power: shotnoise = first.attrs.get('shotnoise', 0) for an AUTO spectrum, 0 for a
+        # cross spectrum; an ArrayMesh carries none (astrild's case: the subtraction at power_spectrum_3d.py:224 is - 0)
+        auto = second is None or second is first
+        shot = float(getattr(first, "shotnoise", 0.0)) if auto else 0.0
         self.attrs = {"mode": mode, "Nmesh": np.array([N] * 3), "BoxSize": np.array([L] * 3),
                       "dk": 2 * np.pi / L if dk is None else dk, "kmin": kmin, "kmax": kmax,
                       "Nmu": 1, "los": list(los), "poles": [], "volume": L ** 3,
-                      "shotnoise": 0.0, "N1": 0, "N2": 0}
+                      "shotnoise": shot, "N1": 0, "N2": 0}
         self.power = BinnedStatistic(["k"], [edges], {"k": res["k"], "power": res["power"],
                                                       "modes": res["modes"]}, dict(self.attrs))
         self.poles = None

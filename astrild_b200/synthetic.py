@@ -91,3 +91,14 @@ def sine_displaced_particles(n_side: int, seed: int, device, rms_cells: float = 
         pos = torch.where(pos >= 1.0, torch.zeros_like(pos), pos)
         cols.append(pos.contiguous())
     return tuple(cols)
+
+
+def halo_subset(pos: tuple, n_halos: int, seed: int, mu: float = math.log(1e13), sigma: float = 1.0) -> tuple:
+    """Config 4: ``n_halos`` positions drawn (with replacement) from the particle columns ``pos`` and log-normal
+    masses exp(N(mu, sigma)) -- a mass-weighted tracer of the same density field.  Returns (x, y, z, mass),
+    float32, on the device of ``pos``."""
+    device = pos[0].device
+    g = torch.Generator(device=device).manual_seed(seed)
+    idx = torch.randint(0, pos[0].numel(), (n_halos,), generator=g, device=device)
+    mass = torch.exp(mu + sigma * torch.randn(n_halos, generator=g, device=device, dtype=torch.float32))
+    return tuple(c[idx].contiguous() for c in pos) + (mass.contiguous(),)

@@ -40,13 +40,55 @@ WORKLOADS = {
     "c3": dict(n=1024, mesh=1024, box=1000.0, resampler="tsc", interlaced=True, compensated=True, seed=31337,
                kind="zeldovich", name="c3: 1024^3 Zel'dovich particles, TSC + interlacing + compensation, 1024^3 mesh"),
 }
+WORKLOADS["c4"] = dict(WORKLOADS["c3"], halos=10 ** 6, halo_seed=7,
+                       name="c4: cross P(k) of 10^6 mass-weighted halos (log-normal masses, drawn from the particles) x 1024^3 "
+                            "Zel'dovich particles, TSC + interlacing + compensation, one 1024^3 mesh geometry")
 WORKLOADS["c5"] = dict(n=2048, mesh=2048, box=1000.0, resampler="cic", interlaced=False, compensated=False, seed=4242,
                        kind="sine", name="c5: 2048^3 particles (lattice + smooth analytic displacement), CIC, 2048^3 mesh, 8 GPUs")
 # diagnostics only (not BASELINE configs): a half-size c3 for profiling, and an incoherent-order c2
 WORKLOADS["c3s"] = dict(WORKLOADS["c3"], n=512, mesh=512, name="c3s: 512^3 particles, TSC + interlacing + compensation, 512^3 mesh (profiling)")
+WORKLOADS["c4s"] = dict(WORKLOADS["c4"], n=512, mesh=512, halos=125000,
+                        name="c4s: cross P(k) of 125000 mass-weighted halos x 512^3 particles, TSC + interlacing + compensation, 512^3 mesh")
 WORKLOADS["c2u"] = dict(WORKLOADS["c2"], kind="uniform", name="c2u: 512^3 uniform-random particles (incoherent order), CIC, 512^3 mesh")
 METRIC = "P(k) pipeline Mparticles/s (deposit+FFT+binning)"
 UNIT = "Mparticles/s"
+
+
+def make_particles(wl: dict, dev, x_planes=None, rank: int = 0, world: int = 1):
+    """-> (pos, halos): the workload's particle columns x, y, z (float32, box units [0,1)) on `dev` -- all of them, or
+    the lattice planes [a, b) of a slab rank -- and, for the cross-spectrum workloads, (x, y, z, mass) of the halos."""
+    from astrild_b200 import synthetic
+    n, L = wl["n"], wl["box"]
+    if wl["kind"] == "zeldovich":
+        pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev, x_planes=x_planes)
+    elif wl["kind"] == "sine":
+        pos = synthetic.sine_displaced_particles(n, wl["seed"], dev, x_planes=x_planes)
+    else:
+        pos = synthetic.uniform_particles(n, wl["seed"], dev)
+        if world > 1:
+            pos = tuple(c[rank::world].contiguous() for c in pos)
+    halos = None
+    if wl.get("halos"):
+        assert x_planes is None, "the halo workloads run on one GPU"
+        halos = synthetic.halo_subset(pos, wl["halos"], wl["halo_seed"])
+    return pos, halos
+
+
+def golden_check(wl_key: str, res: dict, rtol: float = 1e-4):
+    """Compares a result with tests/golden/<workload>_pk.npz (the ORACLE's P(k) of the same particle set, made by
+    tools/make_fixtures.py): mode counts must be equal, <k> within 1e-12, P(k) within rtol per bin.  -> dict or None."""
+    path = os.path.join(ROOT, "tests", "golden", f"{wl_key}_pk.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    ok = np.isfinite(g["power"]) & (g["modes"] > 0)
+    modes_equal = bool(np.array_equal(np.asarray(res["modes"]), g["modes"]))
+    rel = np.abs(np.asarray(res["power"]).real[ok] / g["power"][ok] - 1.0)
+    relk = np.abs(np.asarray(res["k"])[ok] / g["k"][ok] - 1.0)
+    out = {"fixture": os.path.relpath(path, ROOT), "modes_equal": modes_equal, "max_rel_P": float(rel.max()),
+           "max_rel_k": float(relk.max()), "rtol": rtol, "bins": int(ok.sum())}
+    out["ok"] = bool(modes_equal and out["max_rel_P"] <= rtol and out["max_rel_k"] <= 1e-12)
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -147,17 +189,30 @@ def run_reference(args, wl_key: str) -> None:
     state: dict = {}
     for _ in range(args.warmup):
         cpu_step(wl, threads, sp, spl, state)
+    t0 = time.perf_counter()
     times = [cpu_step(wl, threads, sp, spl, state) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
     tot = sum(t["total"] for t in times)
     Np = wl["n"] ** 3
+    N = wl["mesh"]
     value = Np * args.steps / tot / 1e6
+    cfg = {"workload": wl["name"], "particles": Np, "mesh": N, "boxsize": wl["box"], "resampler": wl["resampler"],
+           "interlaced": wl["interlaced"], "compensated": wl["compensated"],
+           "parallelism": "single GPU" if args.gpus == 1 else f"x-slab decomposition over {args.gpus} GPUs",
+           "l2": "inputs >> L2 (126 MB): no flush needed"}
+    if wl.get("halos"):
+        cfg["halos"] = wl["halos"]
+    frac = {"particles": min(sp, Np) / Np, "planes": min(spl, N) / N}
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+           "steps": args.steps, "warmup": args.warmup,
+           # one step = one bounded SAMPLE of the workload (wall time below); `value` is the whole workload's
+           # throughput extrapolated from it stage by stage (deposit ~ particles, FFT and binning ~ planes)
+           "ms_per_step": 1e3 * wall / args.steps, "extrapolated": True, "sample_fraction": frac,
+           "ms_per_step_full_workload_extrapolated": 1e3 * tot / args.steps,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-           "data": "synthetic",
-           "config": {"workload": wl["name"], "particles": Np, "mesh": wl["mesh"], "boxsize": wl["box"]},
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                            "sample": cpu_sample_desc(wl, sp, spl, threads)},
+           "data": "synthetic", "config": cfg,
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "extrapolated": True,
+                            "sample_fraction": frac, "sample": cpu_sample_desc(wl, sp, spl, threads)},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "stages_s": {k: statistics.mean(t[k] for t in times) for k in ("deposit", "fft", "bin")}}
     print(json.dumps(out), flush=True)
@@ -232,65 +287,72 @@ def run_ours(args, wl_key: str) -> None:
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
 
     import astrild_b200 as ab
-    from astrild_b200 import synthetic
 
     wl = WORKLOADS[wl_key]
     n, N, L = wl["n"], wl["mesh"], wl["box"]
     Np = n ** 3
     kmin = 2 * np.pi / L
+    cross = bool(wl.get("halos"))
+    if cross and world > 1:
+        raise SystemExit("bench.py: the cross-spectrum workloads (c4) run on one GPU")
+    Nh = wl.get("halos", 0)
+    n_meshes = 2 if wl["interlaced"] else 1
+    halos = None
 
     if world > 1:
         from astrild_b200 import distributed
         runner = distributed.SlabPk(N, L, resampler=wl["resampler"], interlaced=wl["interlaced"],
                                     compensated=wl["compensated"], device=dev)
-        a, b = runner.lattice_planes(n)
-        if wl["kind"] == "zeldovich":
-            pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev, x_planes=(a, b))
-        elif wl["kind"] == "sine":
-            pos = synthetic.sine_displaced_particles(n, wl["seed"], dev, x_planes=(a, b))
-        else:
-            pos = tuple(c[rank::world].contiguous() for c in synthetic.uniform_particles(n, wl["seed"], dev))
+        pos, _ = make_particles(wl, dev, x_planes=runner.lattice_planes(n), rank=rank, world=world)
         torch.cuda.empty_cache()
 
         def step():
             return runner.power(pos, pos_scale=1.0, kmin=kmin, normalize=True)
 
-        def e2e_step(host_pos):
+        def e2e_step(host_pos, host_halos=None):
             return runner.power(tuple(host_pos), pos_scale=1.0, kmin=kmin, normalize=True)
         eng = runner.eng
         binning = None
         runner.profile = True
     else:
-        if wl["kind"] == "zeldovich":
-            pos = synthetic.zeldovich_particles(n, L, wl["seed"], dev)
-        elif wl["kind"] == "sine":
-            pos = synthetic.sine_displaced_particles(n, wl["seed"], dev)
-        else:
-            pos = synthetic.uniform_particles(n, wl["seed"], dev)
+        pos, halos = make_particles(wl, dev)
         torch.cuda.empty_cache()
         eng = ab.get_engine(N, L, dev)
         comp = (wl["resampler"], wl["interlaced"]) if wl["compensated"] else None
         binning = eng.binning(kmin=kmin, compensation=comp, interlaced=wl["interlaced"])
         mesh1 = eng.new_mesh()
         mesh2 = eng.new_mesh() if wl["interlaced"] else None
+        hmesh1 = eng.new_mesh() if cross else None
+        hmesh2 = eng.new_mesh() if (cross and wl["interlaced"]) else None
         eng.ensure_workspace(Np, False, wl["interlaced"])
-        scale = L ** 3 * (N ** 3 / Np) ** 2 / float(N) ** 6          # normalize=True, unit masses: W = Np
+        s_matter = N ** 3 / Np                                        # normalize=True, unit masses: W = Np
         stage_ev = []
+
+        def deposit_field(p, m, out1, out2, method):
+            if out2 is not None:       # interlaced twins: one shared partition, two tile passes
+                eng.deposit_pair(p, m, wl["resampler"], 1.0, method, out=(out1, out2))
+            else:
+                eng.deposit(p, m, wl["resampler"], 0.0, 1.0, method, out=out1)
 
         def step(record=None):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record is not None else None
             if ev: ev[0].record()
-            if mesh2 is not None:      # interlaced twins: one shared partition, two tile passes
-                eng.deposit_pair(pos, None, wl["resampler"], 1.0, "sorted", out=(mesh1, mesh2))
-            else:
-                eng.deposit(pos, None, wl["resampler"], 0.0, 1.0, "sorted", out=mesh1)
+            deposit_field(pos, None, mesh1, mesh2, "sorted")
             d1 = eng.last_deposit_ms() if record is not None else None
+            s_first = s_matter
+            if cross:                  # the halo catalogue: mass-weighted, small -> the library picks the direct-atomic path
+                hm, hfac = eng.pow2_scaled(halos[3])
+                deposit_field(halos[:3], hm, hmesh1, hmesh2, "auto")
+                s_first = N ** 3 / eng.mesh_sum(hmesh1)           # 1 + delta = mesh / mean: the power-of-two mass unit cancels
             if ev: ev[1].record()
             c1 = eng.r2c(mesh1)
             c1s = eng.r2c(mesh2) if mesh2 is not None else None
+            h1 = eng.r2c(hmesh1) if cross else None
+            h1s = eng.r2c(hmesh2) if hmesh2 is not None else None
             if ev: ev[2].record()
-            raw = eng.bin_power_raw(binning, c1, c1s)
+            raw = eng.bin_power_raw(binning, h1, h1s, c1, c1s) if cross else eng.bin_power_raw(binning, c1, c1s)
             if ev: ev[3].record()
+            scale = L ** 3 * s_first * s_matter / float(N) ** 6
             res = eng.finish(raw, binning, scale)                    # D2H of the shell sums: the result
             if record is not None:
                 b = eng.last_bin_ms(binning)
@@ -298,16 +360,17 @@ def run_ours(args, wl_key: str) -> None:
                        "bin_stage": ev[2].elapsed_time(ev[3]), "bin_kernel": b["bin"], "bin_fold": b["fold"]}
                 for k in d1:
                     rec["dep_" + k] = d1[k]
-                rec["dep_launches"] = 2 if mesh2 is not None else 1
                 record.append(rec)
             return res
 
-        def e2e_step(host_pos):
-            mesh = ab.CatalogMesh(tuple(host_pos), L, N, resampler=wl["resampler"], interlaced=wl["interlaced"],
-                                  compensated=wl["compensated"], normalize=True, pos_scale=1.0, device=dev,
-                                  method="sorted")
-            r = ab.FFTPower(mesh, mode="1d", kmin=kmin)
-            return r.power
+        def e2e_step(host_pos, host_halos=None):
+            kw = dict(resampler=wl["resampler"], interlaced=wl["interlaced"], compensated=wl["compensated"], normalize=True,
+                      pos_scale=1.0, device=dev)
+            matter = ab.CatalogMesh(tuple(host_pos), L, N, method="sorted", **kw)
+            if host_halos is None:
+                return ab.FFTPower(matter, mode="1d", kmin=kmin).power
+            hal = ab.CatalogMesh(tuple(host_halos[:3]), L, N, weight=host_halos[3], **kw)
+            return ab.FFTPower(hal, mode="1d", second=matter, kmin=kmin).power
 
     def barrier():
         torch.cuda.synchronize()
@@ -353,33 +416,42 @@ def run_ours(args, wl_key: str) -> None:
     if clocks is not None:
         clocks["untimed_steps_under_sampler"] = extra_steps
     slab_profile = dict(runner.last_profile) if world > 1 else None
+    slab_info = dict(getattr(runner, "last_info", {})) if world > 1 else None
     ms_per_step = ms / args.steps
     value = Np / (ms_per_step * 1e-3) / 1e6
+    check = golden_check(wl_key, res)            # the timed path's own result against the oracle's fixture
+
+    # ---------------- routing at its design load (N > 1, after the timed region) ---------------
+    routing_stress = None
+    if world > 1 and not args.no_routing_stress and hasattr(runner, "routing_stress"):
+        routing_stress = runner.routing_stress(pos, pos_scale=1.0, kmin=kmin, seed=1234 + rank)
 
     # ---------------- end to end through the public API, host buffers ------------------------
-    if args.no_e2e:
-        h2d = 0
     host_pos = [] if args.no_e2e else [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in pos]
     for h, c in zip(host_pos, pos):
         h.copy_(c)
-    h2d = sum(h.numel() * h.element_size() for h in host_pos) if host_pos else 0
+    host_halos = None
+    if cross and not args.no_e2e:
+        host_halos = [torch.empty(c.shape, dtype=c.dtype, pin_memory=True) for c in halos]
+        for h, c in zip(host_halos, halos):
+            h.copy_(c)
+    h2d = sum(h.numel() * h.element_size() for h in host_pos + (host_halos or []))
     cpu_sp, cpu_planes = 1 << 23, 64
-    cpu_pos = None
-    if world == 1 and not args.no_cpu_baseline:      # the CPU baseline times a prefix of the SAME particles
-        cpu_pos = (torch.stack([c[:cpu_sp] for c in pos], dim=1).double() * L).float().cpu().numpy()
     if world == 1:
         del pos
         torch.cuda.empty_cache()
     e2e_steps = max(1, min(args.steps, 5))
     e2e_s = float("nan")
+    e2e_check = None
     if not args.no_e2e:
-        e2e_step(host_pos)
+        e2e_step(host_pos, host_halos)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            pw = e2e_step(host_pos)
+            pw = e2e_step(host_pos, host_halos)
         barrier()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_check = golden_check(wl_key, pw if isinstance(pw, dict) else pw.data)
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -388,7 +460,9 @@ def run_ours(args, wl_key: str) -> None:
     d2h = 4 * nb1 * 8 + 16
     e2e = None if args.no_e2e else {"value": Np / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d * world) if world > 1 else int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
-           "api": "astrild_b200.CatalogMesh(host x,y,z pinned) -> FFTPower(mode='1d', kmin=2pi/L)"}
+           "api": ("astrild_b200.CatalogMesh(host x,y,z pinned) -> FFTPower(mode='1d', kmin=2pi/L)" if world == 1 else
+                   "astrild_b200.distributed.SlabPk.power(host x,y,z pinned per rank)"),
+           "check": e2e_check}
 
     if rank != 0:
         if world > 1:
@@ -403,31 +477,44 @@ def run_ours(args, wl_key: str) -> None:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    traffic = {}
+    try:                                            # DRAM bytes per launch from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(wl_key, {})
+    except Exception:
+        pass
     roofline, stages = None, None
-    n_meshes = 2 if wl["interlaced"] else 1
+    n_fields = 2 if cross else 1
     if records:
         avg = {k: statistics.mean(r[k] for r in records) for k in records[0]}
-        dep_bytes = Np * 12 + 4 * N ** 3                               # per deposit launch
-        bin_bytes = 8 * N * N * (N // 2 + 1) * n_meshes
-        fft_bytes = (4 * N ** 3 + 8 * N * N * (N // 2 + 1)) * n_meshes
+        dep_bytes = Np * 12 + 4 * N ** 3                               # per tile-kernel launch
+        part_bytes = Np * 12                                           # the partition reads every particle once
+        bin_bytes = 8 * N * N * (N // 2 + 1) * n_meshes * n_fields
+        fft_bytes = (4 * N ** 3 + 8 * N * N * (N // 2 + 1)) * n_meshes * n_fields
         dep_kernel_ms = avg["dep_deposit"] / n_meshes
         cand = {
-            "brick_deposit_kernel": (dep_bytes, dep_kernel_ms),
-            "bin_power_kernel": (bin_bytes, avg["bin_kernel"]),
+            "brick_deposit_pp_kernel": (dep_bytes, dep_kernel_ms, dep_kernel_ms * n_meshes),
+            "brick_partition_kernel": (part_bytes, avg["dep_scatter"], avg["dep_scatter"]),
+            "bin_power_kernel": (bin_bytes, avg["bin_kernel"], avg["bin_kernel"]),
         }
-        name = max(cand, key=lambda k: cand[k][1] * (n_meshes if k == "brick_deposit_kernel" else 1))
-        by, t = cand[name]
+        if avg.get("dep_count", 0.0) > 0.0:
+            cand["brick_count_kernel"] = (part_bytes, avg["dep_count"], avg["dep_count"])
+        name = max(cand, key=lambda k: cand[k][2])                     # the kernel with the largest share of the step
+        by, t, _ = cand[name]
         roofline = {"bound": "hbm", "kernel": name, "achieved": by / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                    "frac": by / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": by, "ms_per_launch": t}
+                    "frac": by / (t * 1e-3) / 1e9 / peak, "traffic": traffic.get(name), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": by, "ms_per_launch": t,
+                    "launches_per_step": n_meshes if name == "brick_deposit_pp_kernel" else 1}
+        stage_bytes = Np * 12 + 4 * N ** 3 * n_meshes                  # SURVEY 8(d) B_dep of the matter field
         stages = {
-            "ms": {k: round(v, 4) for k, v in avg.items() if k != "dep_launches"},
-            "deposit_stage_GBps": n_meshes * dep_bytes / (avg["deposit_stage"] * 1e-3) / 1e9,
+            "ms": {k: round(v, 4) for k, v in avg.items()},
+            "deposit_stage_GBps": stage_bytes / (avg["deposit_stage"] * 1e-3) / 1e9,
+            "deposit_stage_frac": stage_bytes / (avg["deposit_stage"] * 1e-3) / 1e9 / peak,
             "fft_GBps_algorithmic": fft_bytes / (avg["fft"] * 1e-3) / 1e9,
             "bin_kernel_GBps": bin_bytes / (avg["bin_kernel"] * 1e-3) / 1e9,
             "bin_kernel_frac": bin_bytes / (avg["bin_kernel"] * 1e-3) / 1e9 / peak,
-            "brick_deposit_GBps": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9,
-            "brick_deposit_frac": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9 / peak,
+            "tile_kernel_GBps": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9,
+            "tile_kernel_frac": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9 / peak,
+            "kernel_fracs": {k: round(v[0] / (v[1] * 1e-3) / 1e9 / peak, 4) for k, v in cand.items()},
         }
 
     # ---------------- CPU baseline beside it (rank 0, N = 1 only) ----------------------------
@@ -435,44 +522,73 @@ def run_ours(args, wl_key: str) -> None:
     if world == 1 and not args.no_cpu_baseline:
         from oracle import pk_oracle_fast as f
         f.build()
-        t = cpu_step(wl, 1, cpu_sp, cpu_planes, {"pos": cpu_pos})
+        t = cpu_step(wl, 1, cpu_sp, cpu_planes, {})     # same sample generator (and prefix) as --impl reference
         cpu = {"value": Np / t["total"] / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": cpu_sample_desc(wl, cpu_sp, cpu_planes, 1), "seconds_scaled": {k: round(v, 2) for k, v in t.items()}}
+               "sample": cpu_sample_desc(wl, cpu_sp, cpu_planes, 1), "extrapolated": True,
+               "sample_fraction": {"particles": min(cpu_sp, Np) / Np, "planes": min(cpu_planes, N) / N},
+               "seconds_scaled": {k: round(v, 2) for k, v in t.items()}}
 
+    roofline_nvlink = None
     if world > 1 and dep_ms_rank0 is not None:
         # rank 0's share: its particles and its n0 planes per launch; the tile kernel shares the SMs with the first
         # mesh's FFT / transpose (side stream), so this is its time inside the step, not alone
         np_rank, planes = pos[0].numel(), N // world
         dep_bytes = np_rank * 12 + 4 * planes * N * N
         t = dep_ms_rank0["deposit"] / n_meshes
-        roofline = {"bound": "hbm", "kernel": "brick_deposit_kernel", "achieved": dep_bytes / (t * 1e-3) / 1e9, "peak": peak,
+        roofline = {"bound": "hbm", "kernel": "brick_deposit_pp_kernel", "achieved": dep_bytes / (t * 1e-3) / 1e9, "peak": peak,
                     "unit": "GB/s", "frac": dep_bytes / (t * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": dep_bytes, "ms_per_launch": t, "rank": 0,
                     "deposit_kernels_ms_rank0": {k: round(v, 4) for k, v in dep_ms_rank0.items()}}
-    # hand-written kernels per step and rank.  1 GPU: count, segment sums, scan, scatter, one tile kernel per mesh,
-    # bin, fold.  Slab path: route (stage, scan, group) + those + the received particles (one RED kernel per mesh)
-    # + 2 ghost-plane adds per mesh + one peer-store transpose per mesh.
+        # NVLink: bytes this rank sends to its peers per step in the x<->y transposes, over the time of the
+        # peer-store kernels (CUDA events on their stream), against 900 GB/s per direction (NVLink 5)
+        if slab_info and slab_info.get("transpose_ms"):
+            out_bytes = 8 * (N // world) * N * (N // 2 + 1) * (world - 1) / world * n_meshes
+            tms = slab_info["transpose_ms"]
+            roofline_nvlink = {"bound": "nvlink", "kernel": "transpose_p2p_kernel" if slab_info.get("transpose") == "p2p-store" else "nccl all-to-all",
+                               "bytes_out_per_gpu_per_step": out_bytes, "ms_per_step": tms,
+                               "achieved": out_bytes / (tms * 1e-3) / 1e9, "peak": 900.0, "unit": "GB/s",
+                               "frac": out_bytes / (tms * 1e-3) / 1e9 / 900.0, "peak_source": "NVLink 5 nominal, per direction"}
+    # hand-written kernels per step and rank.  1 GPU: partition (scatter), scan x2, one tile kernel per mesh, bin, fold
+    # (+ count when the two-pass partition is selected).  Slab path: route (stage, scan, group) + those + the received
+    # particles (one RED kernel per mesh) + 2 ghost-plane adds per mesh + one peer-store transpose per mesh.
     kernels_per_step = (4 + n_meshes + 2) if world == 1 else (3 + 4 + n_meshes + 2 + n_meshes + 2 * n_meshes + n_meshes)
+    if cross:
+        kernels_per_step += n_meshes + 1             # halo catalogue: one direct-atomic kernel per mesh + the mass sum
+    config = {"workload": wl["name"], "particles": Np, "mesh": N, "boxsize": L, "resampler": wl["resampler"],
+              "interlaced": wl["interlaced"], "compensated": wl["compensated"],
+              "parallelism": "single GPU" if world == 1 else f"x-slab decomposition over {world} GPUs",
+              "l2": "inputs >> L2 (126 MB): no flush needed"}
+    if cross:
+        config["halos"] = Nh
+    if world > 1 and slab_info:
+        config["transpose"] = slab_info.get("transpose")
+        config["critical_path"] = slab_info.get("critical_path")
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "f32 mesh/FFT, f64 index + shell sums", "data": "synthetic",
-           "config": {"workload": wl["name"], "particles": Np, "mesh": N, "boxsize": L, "resampler": wl["resampler"],
-                      "interlaced": wl["interlaced"], "compensated": wl["compensated"],
-                      "parallelism": "single GPU" if world == 1 else f"x-slab decomposition over {world} GPUs",
-                      "l2": "inputs >> L2 (126 MB): no flush needed"},
+           "config": config,
            "clocks": clocks, "e2e": e2e,
            "gpu_launches": kernels_per_step * args.steps * world,
-           "gpu_launches_note": "hand-written kernels in the timed region, all ranks: per step and rank brick count + segment sums + scan + scatter "
-                                "(shared by the interlaced twins), one brick deposit per mesh, bin + fold"
+           "gpu_launches_note": "hand-written kernels in the timed region, all ranks: per step and rank brick partition + segment sums + scan "
+                                "(shared by the interlaced twins), one tile kernel per mesh, bin + fold"
                                 + ("" if world == 1 else "; plus route stage/scan/group, one RED deposit per mesh for the received "
                                    "particles, ghost-plane adds and one peer-store transpose per mesh") +
                                 "; cuFFT, NCCL and torch kernels are not counted",
            "roofline": roofline, "stages": stages if world == 1 else {"ms_rank0_last_step": {k: round(v, 3) for k, v in slab_profile.items()}},
            "cpu_baseline": cpu,
-           "check": {"first_bins_P": [float(x) for x in res["power"].real[:3]], "modes0": int(res["modes"][0])}}
+           "check": dict(check or {"fixture": None, "ok": None},
+                         first_bins_P=[float(x) for x in res["power"].real[:3]], modes0=int(res["modes"][0]))}
+    if roofline_nvlink is not None:
+        out["roofline_nvlink"] = roofline_nvlink
+    if routing_stress is not None:
+        out["routing_stress"] = routing_stress
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    bad = [c for c in (check, e2e_check) if c is not None and not c["ok"]]
+    if bad:
+        sys.stderr.write(f"bench.py: result differs from the oracle fixture: {bad}\n")
+        sys.exit(3)
 
 
 def pick_workload(args) -> str:
@@ -500,6 +616,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (diagnostic runs only)")
+    ap.add_argument("--no-routing-stress", action="store_true", help="N > 1: skip the unsorted-input run after the timed region")
     args = ap.parse_args()
     # whole-run watchdog: a dead-lock (collectives, device-side barriers) must not hold the GPUs for long
     limit = int(os.environ.get("APK_BENCH_TIME_LIMIT_S", "1500"))

@@ -134,39 +134,67 @@ def power_from_mesh(value_map1, value_map2, L: float, workers: int = 1, threads:
     return r["k"], r["power"].real - 0.0, r["modes"]
 
 
+def _combine_compensate_inplace(c, c2, N: int, L: float, resampler: str, interlaced: bool, compensated: bool):
+    """pk_oracle.interlace_combine followed by pk_oracle.compensate, x-slab by x-slab and in place (same
+    expressions in the same order per element), so that a 1024^3 field needs no third and fourth full-size
+    temporary.  c2 is consumed."""
+    kx, ky, kz = _o.k_tables(N, L)
+    H = L / N
+    f = _o.compensation_1d(resampler, interlaced, N) if compensated else None
+    for ix in range(N):
+        if interlaced:
+            kH = (kx[ix] + ky[:, None] + kz[None, :]) * H
+            c[ix] = 0.5 * c[ix] + 0.5 * c2[ix] * np.exp(0.5j * kH)
+        if compensated:
+            c[ix] = c[ix] / (f[ix] * f[:, None] * f[None, : N // 2 + 1])
+    return c
+
+
 def power_from_particles(pos, mass, N: int, L: float, resampler: str = "tsc",
                          interlaced: bool = False, compensated: bool = False,
                          normalize: bool = False, workers: int = 1, threads: int = 1,
-                         pos2=None, mass2=None, timings: dict | None = None):
-    """Twin of pk_oracle.power_from_particles (stats_subfind.py:125-150 + CatalogMesh options)."""
+                         pos2=None, mass2=None, timings: dict | None = None, paint_L: float | None = None,
+                         lean: bool = False):
+    """Twin of pk_oracle.power_from_particles (stats_subfind.py:125-150 + CatalogMesh options).
+
+    paint_L: box length in the units of ``pos`` when they differ from L (Ramses-style [0,1) coordinates:
+    paint_L = 1), so that the float32 positions reach the window arithmetic unrescaled.
+    lean: free every full-size array as soon as it is dead and combine / compensate in place (BASELINE sizes)."""
     import time
 
     t = {"deposit": 0.0, "fft": 0.0, "bin": 0.0}
+    pL = L if paint_L is None else paint_L
 
     def field(p, m):
         dx = L / N
         t0 = time.perf_counter()
-        real = paint(p, m, N, L, resampler, threads=threads)
+        real = paint(p, m, N, pL, resampler, threads=threads)
         t["deposit"] += time.perf_counter() - t0
         scale = (N ** 3 / real.sum()) if normalize else 1.0 / dx ** 3
         t0 = time.perf_counter()
         c = _o.r2c(real, workers)
         t["fft"] += time.perf_counter() - t0
+        del real
         c *= scale
+        c2_ = None
         if interlaced:
             t0 = time.perf_counter()
-            real2 = paint(p, m, N, L, resampler, shift=0.5, threads=threads)
+            real2 = paint(p, m, N, pL, resampler, shift=0.5, threads=threads)
             t["deposit"] += time.perf_counter() - t0
             t0 = time.perf_counter()
             c2_ = _o.r2c(real2, workers)
             t["fft"] += time.perf_counter() - t0
-            t0 = time.perf_counter()
-            c = _o.interlace_combine(c, c2_ * scale, N, L)
-            t["bin"] += time.perf_counter() - t0
-        if compensated:
-            t0 = time.perf_counter()
-            c = _o.compensate(c, resampler, interlaced, N)
-            t["bin"] += time.perf_counter() - t0
+            del real2
+            c2_ *= scale
+        t0 = time.perf_counter()
+        if lean:
+            c = _combine_compensate_inplace(c, c2_, N, L, resampler, interlaced, compensated)
+        else:
+            if interlaced:
+                c = _o.interlace_combine(c, c2_, N, L)
+            if compensated:
+                c = _o.compensate(c, resampler, interlaced, N)
+        t["bin"] += time.perf_counter() - t0
         return c
 
     c1 = field(pos, mass)
