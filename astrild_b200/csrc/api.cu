@@ -2,6 +2,7 @@
 #include "apk_common.cuh"
 #include <cstdlib>
 #include "deposit_common.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -24,6 +25,9 @@ int deposit_atomic_launch(const void *, const void *, const void *, int, int, co
 int deposit_sorted_launch(apk_plan *, const void *, const void *, const void *, int, int, const void *, int,
                           long long, int, const DepositGeom &, float *, float *, cudaStream_t);
 size_t deposit_sorted_workspace_bytes(const apk_plan *, long long np, int with_mass, int pair);
+int deposit_paged_launch(apk_plan *, const void *, const void *, const void *, int, int, const void *, int,
+                         long long, int, const DepositGeom &, float *, float *, cudaStream_t);
+size_t deposit_paged_workspace_bytes(const apk_plan *, long long np, int with_mass, int pair);
 int mesh_sum_launch(apk_plan *, const void *, int, double *, cudaStream_t);
 int padded_mesh_sum_launch(apk_plan *, const float *, double *, cudaStream_t);
 int load_mesh_launch(apk_plan *, const void *, int, double, float *, cudaStream_t);
@@ -144,7 +148,8 @@ int apk_plan_ghost_planes(const apk_plan *P, int *n_lo, int *n_hi) {
 
 int apk_plan_workspace_bytes(const apk_plan *P, int64_t max_particles, int with_mass, int interlaced, size_t *bytes) {
     APK_REQUIRE(P && bytes, "apk_plan_workspace_bytes: null argument");
-    size_t dep = deposit_sorted_workspace_bytes(P, max_particles, with_mass, interlaced);
+    size_t dep = std::max(deposit_sorted_workspace_bytes(P, max_particles, with_mass, interlaced),
+                          deposit_paged_workspace_bytes(P, max_particles, with_mass, interlaced));
     // the cuFFT work areas sit at the END of the workspace, one per plan, disjoint from the deposit's region at
     // its start: a transform may run on another stream while a deposit is in flight
     *bytes = ((dep + 255) & ~(size_t)255) + P->fft_work_bytes + 512;
@@ -195,8 +200,12 @@ static int deposit_impl(apk_plan *P, const void *p0, const void *p1, const void 
         method = (np >= (1 << 18) && (double)np >= 16.0 * bricks) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
     }
     if (P->timing) P->dep_timed = false;            // an untimed call leaves the last timed deposit's events alone
-    if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
-        return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
+    if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0) {
+        static const bool two_pass = [] { const char *e = getenv("APK_PARTITION"); return e && !strcmp(e, "twopass"); }();
+        if (two_pass)
+            return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
+        return deposit_paged_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
+    }
     if (P->mark(3, st)) { set_error("apk_deposit: event record failed"); return 1; }
     int rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
     if (rc) return rc;
