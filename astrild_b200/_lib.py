@@ -57,6 +57,15 @@ SIGNATURES = {
     "apk_binning_create": [ct.POINTER(_vp), _vp, _i, _i, _i] + [_vp] * 5 + [_i] + [_vp] * 6 + [_i, _i],
     "apk_binning_destroy": [_vp],
     "apk_bin_power": [_vp] * 9 + [_vp],
+    "apk_tables_k_axis": [_i, _d, _i, _vp],
+    "apk_tables_k_edges": [_i, _d, _d, _d, _d, _vp, _i, ct.POINTER(_i)],
+    "apk_tables_hermitian_weights": [_i, _vp],
+    "apk_tables_compensation": [_i, _i, _i, _vp],
+    "apk_tables_interlace_phase": [_i, _d, _vp],
+    "apk_power_scratch_elems": [_vp, _i, _i, ct.POINTER(_i64)],
+    "apk_power_from_particles": [_vp, _vp, _vp, _vp, _i, _i, _d, _vp, _i, _i64, _i, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp,
+                                 _i, ct.POINTER(_i), ct.POINTER(_d), _vp],
+    "apk_power_from_mesh": [_vp, _vp, _vp, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _i, ct.POINTER(_i), _vp],
 }
 
 _lib = None

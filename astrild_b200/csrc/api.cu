@@ -25,9 +25,7 @@ int deposit_atomic_launch(const void *, const void *, const void *, int, int, co
 int deposit_sorted_launch(apk_plan *, const void *, const void *, const void *, int, int, const void *, int,
                           long long, int, const DepositGeom &, float *, float *, cudaStream_t);
 size_t deposit_sorted_workspace_bytes(const apk_plan *, long long np, int with_mass, int pair);
-int deposit_paged_launch(apk_plan *, const void *, const void *, const void *, int, int, const void *, int,
-                         long long, int, const DepositGeom &, float *, float *, cudaStream_t);
-size_t deposit_paged_workspace_bytes(const apk_plan *, long long np, int with_mass, int pair);
+
 int mesh_sum_launch(apk_plan *, const void *, int, double *, cudaStream_t);
 int padded_mesh_sum_launch(apk_plan *, const float *, double *, cudaStream_t);
 int load_mesh_launch(apk_plan *, const void *, int, double, float *, cudaStream_t);
@@ -38,6 +36,8 @@ int accumulate_launch(apk_plan *, float *, const float *, long long, cudaStream_
 int transpose_p2p_launch(apk_plan *, const void *, const unsigned long long *, long long, int, cudaStream_t);
 int bin_power_launch(apk_binning *, const void *, const void *, const void *, const void *, double *,
                      double *, double *, int64_t *, cudaStream_t);
+
+void forget_plan_binnings(apk_plan *P);
 
 static int make_fft3d(apk_plan *P) {
     if (P->has_fft3d) return 0;
@@ -125,6 +125,7 @@ int apk_plan_create(apk_plan **out, int nmesh, double boxsize, int x0, int n0, i
 int apk_plan_destroy(apk_plan *P) {
     if (!P) return 0;
     DeviceGuard guard(P->device);
+    forget_plan_binnings(P);                     // binning objects made by apk_power_from_*
     if (P->has_fft3d) cufftDestroy(P->fft3d);
     if (P->has_fft2d) cufftDestroy(P->fft2d);
     if (P->has_fft1d) cufftDestroy(P->fft1d);
@@ -148,8 +149,7 @@ int apk_plan_ghost_planes(const apk_plan *P, int *n_lo, int *n_hi) {
 
 int apk_plan_workspace_bytes(const apk_plan *P, int64_t max_particles, int with_mass, int interlaced, size_t *bytes) {
     APK_REQUIRE(P && bytes, "apk_plan_workspace_bytes: null argument");
-    size_t dep = std::max(deposit_sorted_workspace_bytes(P, max_particles, with_mass, interlaced),
-                          deposit_paged_workspace_bytes(P, max_particles, with_mass, interlaced));
+    size_t dep = deposit_sorted_workspace_bytes(P, max_particles, with_mass, interlaced);
     // the cuFFT work areas sit at the END of the workspace, one per plan, disjoint from the deposit's region at
     // its start: a transform may run on another stream while a deposit is in flight
     *bytes = ((dep + 255) & ~(size_t)255) + P->fft_work_bytes + 512;
@@ -200,12 +200,8 @@ static int deposit_impl(apk_plan *P, const void *p0, const void *p1, const void 
         method = (np >= (1 << 18) && (double)np >= 16.0 * bricks) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
     }
     if (P->timing) P->dep_timed = false;            // an untimed call leaves the last timed deposit's events alone
-    if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0) {
-        static const bool two_pass = [] { const char *e = getenv("APK_PARTITION"); return e && !strcmp(e, "twopass"); }();
-        if (two_pass)
-            return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
-        return deposit_paged_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
-    }
+    if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
+        return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
     if (P->mark(3, st)) { set_error("apk_deposit: event record failed"); return 1; }
     int rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);
     if (rc) return rc;
@@ -440,7 +436,11 @@ int apk_binning_create(apk_binning **out, apk_plan *P, int n_a, int n_b, int nz,
     B->wz = df;
     if (has_comp) { B->icomp2_a = df + nz; B->icomp2_b = B->icomp2_a + n_a; B->icomp2_z = B->icomp2_b + n_b; }
 
-    if (const char *v = getenv("APK_BIN_TABLE")) B->use_table = v[0] == '1' && nedges < 65534;      // experimental
+    // the binning PLAN: shell of every mode (uint16), mode counts and sum(w k) per shell are functions of the geometry
+    // alone; they are computed on the device by the first apk_bin_power of this object (same float64 digitize) and the
+    // data passes then read the table instead of redoing float64 wavenumber arithmetic.  APK_BIN_TABLE=0: one-pass kernel.
+    B->use_table = nedges < 65534;
+    if (const char *v = getenv("APK_BIN_TABLE")) B->use_table = B->use_table && v[0] != '0';
     B->partial_ctas = P->num_sms * 3;   // = resident CTAs (80 regs, 51 KB smem)
     const size_t pbytes = sizeof(double) * 4 * (size_t)B->partial_ctas * (nedges + 1);
     if (cudaMalloc(&B->partial, pbytes) != cudaSuccess) {

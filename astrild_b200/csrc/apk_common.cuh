@@ -95,7 +95,7 @@ struct apk_binning {
     float *icomp2_a = nullptr, *icomp2_b = nullptr, *icomp2_z = nullptr;   // 1 / comp^2
     float2 *ph_a = nullptr, *ph_b = nullptr, *ph_z = nullptr;              // exp(i phase)
     double kmin_guess = 0.0, inv_dk_guess = 0.0;   // uniform-edge guess for the bin search
-    // experimental table-driven binning (APK_BIN_TABLE=1): shell of every mode, and [ksum | - | - | nmodes] of the geometry pass
+    // table-driven binning (default; APK_BIN_TABLE=0 disables): shell of every mode, and [ksum | - | - | nmodes] of the geometry pass
     bool use_table = false;
     unsigned short *bins = nullptr;
     double *geo = nullptr;

@@ -60,7 +60,7 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *addr, unsigned l
 template <bool INTERLACED, bool CROSS>
 struct BinRows { static constexpr int TA = (INTERLACED || CROSS) ? 2 : 4; };
 
-// MODE 0: everything in one pass (the default).  Experimental split (APK_BIN_TABLE=1): the shell of a mode, the mode
+// MODE 0: everything in one pass (APK_BIN_TABLE=0).  Default split: the shell of a mode, the mode
 // counts and sum(w k) depend on the binning alone, so MODE 1 computes them once per binning object -- same float64
 // digitize, no grid read -- and stores the shell of every mode as uint16; MODE 2, run per spectrum, reads that
 // table instead of doing any float64 wavenumber arithmetic and only accumulates sum(w P).
@@ -378,7 +378,7 @@ int bin_power_launch(apk_binning *B, const void *c1, const void *c1s, const void
     const size_t smem = bin_smem_bytes(B->nedges);
     const bool comp = B->has_comp;
 
-    // experimental (APK_BIN_TABLE=1): geometry once per binning object, then table-driven data passes
+    // geometry once per binning object (the binning plan), then table-driven data passes
     const bool tabled = B->use_table;
     if (tabled && !B->bins) {
         const size_t modes = (size_t)B->n_a * B->n_b * B->nz;

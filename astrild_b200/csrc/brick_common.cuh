@@ -1,5 +1,5 @@
 // Brick geometry, brick keys and payload conventions shared by the partition and tile kernels of the sorted deposit
-// (deposit_sorted.cu: two-pass partition, contiguous buckets; deposit_paged.cu: one-pass partition, paged buckets).
+// (deposit_sorted.cu).
 #pragma once
 #include "apk_common.cuh"
 #include "deposit_common.cuh"
@@ -9,28 +9,11 @@
 
 namespace apk {
 
-// one turn of a spin loop that waits for another thread's store (the CPU test harness yields to the other fibers)
-__device__ __forceinline__ void spin_pause() {
-#ifdef APK_SIMT
-    simt::yield();
-#endif
-}
-
-constexpr int BX = 12, BY = 6;                  // brick edge in cells along x, y (multiples of 3)
+constexpr int BX = 12, BY = 6;                  // brick edge in cells along x, y
 constexpr int BZ = 32;                          // z-lanes of a column = tile cells along z (one warp)
 // home cells along z: 32 - (S-1), so that a column's 32 lanes are exactly its 32 tile cells
 // (30 home cells + 2 halo lanes for TSC, 31 + 1 for CIC) and the spread needs no halo special case
 template <int S> struct BrickZ { static constexpr int CELLS = BZ - (S - 1); };
-constexpr int BRICK_CELLS = BX * BY * BZ;       // 2304 count slots (halo lanes stay empty)
-constexpr int DEP_THREADS = 256;                // 8 warps, each owns a 3 x 3 block of (x,y) columns
-#ifndef APK_DEP_CTAS
-#define APK_DEP_CTAS 3
-#endif
-
-constexpr int DEP_CTAS_PER_SM = APK_DEP_CTAS;   // 3: 24 warps per SM at <= 85 registers
-constexpr int CH = 3072;                        // particles per shared-memory chunk
-static_assert(DEP_THREADS / 32 == (BX / 3) * (BY / 3), "one warp per 3 x 3 block of columns");
-
 struct P3 { float x, y, z; };
 struct P4 { float x, y, z, m; };
 

@@ -13,7 +13,7 @@
 //                           equal keys (snapshot order is spatially coherent).  float32 positions use an
 //                           error-free float32 product (no FP64 issue slots), float64 positions the oracle's
 //                           float64 expression; both put every particle in the oracle's cell.
-//   2. brick_scan_kernel    exclusive scan of the counts -> brick_start[], cursors.
+//   2. brick_scan_kernel    exclusive scan of the counts -> brick_start[], cursors, list of non-empty bricks.
 //   3. brick_scatter_kernel keys are recomputed (never stored); each run of equal keys claims its slots with ONE
 //                           atomicAdd on the brick's cursor and writes its payload = brick-local coordinates as
 //                           3 floats (+ mass), contiguously.  One read and one write of the particles replace a
@@ -21,22 +21,16 @@
 //      PAIR mode (apk_deposit_interlaced): one partition serves both interlaced meshes -- particles whose
 //      two home cells fall in different bricks are filed twice, sign bits of the payload say which
 //      mesh a copy is for.
-//   4. brick_deposit_kernel persistent CTAs (8 warps, 3 per SM) pull bricks from a counter; per brick and per
-//      chunk of <= CH particles: counting-sort the chunk by home cell inside shared memory (native 32-bit
-//      ATOMS.ADD gives each particle its rank), then one thread per home cell sums the S^3 window moments of
-//      its own particles in registers (packed FFMA2).  The moments are spread WITHOUT atomics and WITHOUT
-//      shared memory (shared-memory float atomics are CAS loops on sm_100): every warp owns a 3 x 3 block of
-//      (x,y) columns, its 32 lanes are the 32 cells of a column along z (30 home cells + 2 halo lanes for
-//      TSC), so the z-spread is two warp shuffles with no edge cases and the (x,y)-spread is an add into the
-//      warp's 5 x 5 (TSC) window of registers with compile-time indices.  No barrier separates the columns:
-//      warps run through their 9 columns independently.  The window then goes to the mesh as one coalesced
-//      128-byte RED.ADD.F32 per (x,y) column, zeros skipped; bricks are visited x-major so neighbouring
-//      windows meet in L2.
+//   4. brick_tile_kernel    one CTA per non-empty brick, one THREAD per particle, the brick's window of the mesh as
+//                           fixed-point integers in shared memory, native ATOMS.ADD (see the kernel's comment).
+//      A one-pass partition into paged buckets (pages handed out as the cursors cross page boundaries, no count
+//      pass) was built and measured in round 2: 21.7 ms against 7.5 + 9.4 ms for count + scatter at 1024^3 -- the
+//      page-table look-up sits on the store's critical path -- and its wait for a page that another thread has yet to
+//      publish can dead-lock when a thread's two in-flight claims complete out of order (it did, on randomly ordered
+//      input).  It was removed; profiles/r02_measurements.md has the numbers.
 #include "brick_common.cuh"
 #include <algorithm>
 #include <cstdint>
-#include <cstdlib>
-#include <cstring>
 #include <type_traits>
 
 namespace apk {
@@ -220,313 +214,36 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
     }
 }
 
-// dynamic shared memory layout of brick_deposit_kernel
-template <bool MASS>
-struct DepSmem {
-    static constexpr int cnt_ints = BRICK_CELLS + 1;
-    static constexpr size_t bytes = sizeof(int) * (cnt_ints + 64) + sizeof(float) * CH * (MASS ? 4 : 3) + 64;
-};
-
-// Window moments of the particles of one home cell, accumulated with packed FFMA2.
-// Layout: A[a][c] = float2 over the b-pair (first, last) of the window; for TSC the middle b is kept as
-// B2[a] = float2 over the c-pair (first, last) and B1[a] = the centre (b = c = middle): 27 moments in 12 packed and 3
-// scalar accumulators, 15 FMA instructions per particle.  The per-axis weights are formed the same way, the two outer
-// ones of an axis as one float2: 0.5 (0.5 -+ d)^2 = (s/2 -+ s d)^2 with s = sqrt(1/2).
-template <int S, bool MASS>
-struct Moments {
-    float2 A[S][S];
-    float2 B2[S];     // TSC only
-    float B1[S];      // TSC only
-
-    // outer weights of one axis as a pair (first, last), and the middle one (TSC; CIC has no middle)
-    __device__ __forceinline__ static void axis(float d, float2 &wp, float &wm) {
-        if (S == 2) {
-            wp = make_float2(1.f - d, d);
-            wm = 0.f;
-        } else {
-            const float s = 0.70710678118654752f;
-            const float2 t = __ffma2_rn(make_float2(-s, s), make_float2(d, d), make_float2(0.5f * s, 0.5f * s));
-            wp = __fmul2_rn(t, t);
-            wm = fmaf(-d, d, 0.75f);
-        }
-    }
-
-    // FIRST: the particle sets the moments (no zeroing pass); otherwise it is added.  !valid (FIRST only): the cell
-    // is empty and everything becomes zero; its coordinates are whatever the list holds at that slot, hence the selects.
-    template <bool FIRST>
-    __device__ __forceinline__ void put(float dx, float dy, float dz, float m, bool valid) {
-        float2 wxp, wyp, wzp;
-        float wxm, wym, wzm;
-        axis(FIRST && !valid ? 0.f : dx, wxp, wxm);
-        axis(FIRST && !valid ? 0.f : dy, wyp, wym);
-        axis(FIRST && !valid ? 0.f : dz, wzp, wzm);
-        if (MASS) { wxp = __fmul2_rn(wxp, make_float2(m, m)); wxm *= m; }
-        if (FIRST && !valid) { wxp = make_float2(0.f, 0.f); wxm = 0.f; }
-        const float wx[3] = {wxp.x, wxm, wxp.y};              // index S - 1 of CIC is .y
-        const float wz[3] = {wzp.x, wzm, wzp.y};
-#pragma unroll
-        for (int a = 0; a < S; ++a) {
-            const float w = (a == S - 1) ? wx[2] : wx[a];
-            const float2 wxy = __fmul2_rn(make_float2(w, w), wyp);
-#pragma unroll
-            for (int c = 0; c < S; ++c) {
-                const float z = (c == S - 1) ? wz[2] : wz[c];
-                A[a][c] = FIRST ? __fmul2_rn(wxy, make_float2(z, z)) : __ffma2_rn(wxy, make_float2(z, z), A[a][c]);
-            }
-        }
-        if (S == 3) {
-            const float2 mp = __fmul2_rn(wxp, make_float2(wym, wym));      // (wx0 wym, wx2 wym)
-            const float mm = wxm * wym;
-            const float wm[3] = {mp.x, mm, mp.y};
-#pragma unroll
-            for (int a = 0; a < S; ++a) {
-                B2[a] = FIRST ? __fmul2_rn(make_float2(wm[a], wm[a]), wzp) : __ffma2_rn(make_float2(wm[a], wm[a]), wzp, B2[a]);
-                B1[a] = FIRST ? wm[a] * wzm : fmaf(wm[a], wzm, B1[a]);
-            }
-        }
-    }
-
-    __device__ __forceinline__ void add(float dx, float dy, float dz, float m) { put<false>(dx, dy, dz, m, true); }
-    __device__ __forceinline__ void init(float dx, float dy, float dz, float m, bool valid) { put<true>(dx, dy, dz, m, valid); }
-
-    // moment of window offset (a, b, c)
-    __device__ __forceinline__ float get(int a, int b, int c) const {
-        if (b == 0) return A[a][c].x;
-        if (b == S - 1) return A[a][c].y;
-        if (c == 0) return B2[a].x;
-        if (c == S - 1) return B2[a].y;
-        return B1[a];
-    }
-};
-
-// Counting sort of one chunk of <= CHUNK brick-ordered particles by home cell, inside shared memory: cnt[] becomes the
-// exclusive scan of the per-cell counts (cnt[cell] .. cnt[cell + 1] = that cell's particles), sx / sy / sz (/ sm)
-// the brick-local coordinates in cell order.  Called by all threads of the CTA; ends with a barrier.
-template <int S, bool MASS, typename VT, int CHUNK>
-__device__ __forceinline__ void sort_chunk_by_cell(const VT *__restrict__ vals, unsigned int c0, int nchunk, int sel,
-                                                   int *cnt, int *wsum, float *sx, float *sy, float *sz, float *sm) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int OFF = (S == 3) ? 1 : 0;
-    constexpr int PPT = CHUNK / DEP_THREADS;                 // particles per thread per chunk
-    constexpr int NBATCH = PPT % 3 == 0 ? 3 : 2, BATCH = PPT / NBATCH;   // loads are issued BATCH at a time before first use
-    static_assert(BATCH * NBATCH == PPT && PPT * DEP_THREADS == CHUNK, "chunk size must divide into the load batches");
-    for (int i = tid; i <= BRICK_CELLS; i += DEP_THREADS) cnt[i] = 0;
-    __syncthreads();
-
-    // ---- rank my particles inside their home cell (cell | rank << 13 kept in a register;
-    //      the coordinates are re-read from L1/L2 in the scatter pass to save registers).
-    //      Loads are issued in batches before first use to overlap their latency.
-    int packed[PPT];
-#pragma unroll
-    for (int h = 0; h < NBATCH; ++h) {
-        VT v[BATCH];
-#pragma unroll
-        for (int k = 0; k < BATCH; ++k) {
-            const int i = (h * BATCH + k) * DEP_THREADS + tid;
-            v[k] = vals[c0 + min(i, nchunk - 1)];
-        }
-#pragma unroll
-        for (int k = 0; k < BATCH; ++k) {
-            const int i = (h * BATCH + k) * DEP_THREADS + tid;
-            const bool keep = unpack_pair(v[k], sel);
-            int hx, hy, hz;
-            if (S == 2) { hx = (int)floorf(v[k].x); hy = (int)floorf(v[k].y); hz = (int)floorf(v[k].z); }
-            else        { hx = (int)floorf(v[k].x + 0.5f); hy = (int)floorf(v[k].y + 0.5f); hz = (int)floorf(v[k].z + 0.5f); }
-            hx = max(0, min(hx, BX - 1)); hy = max(0, min(hy, BY - 1)); hz = max(0, min(hz, BrickZ<S>::CELLS - 1));
-            const int cell = (hx * BY + hy) * BZ + hz + OFF;          // z-lane = home z + OFF
-            packed[h * BATCH + k] = -1;
-            if (i < nchunk && keep) packed[h * BATCH + k] = cell | (atomicAdd(&cnt[cell], 1) << 13);
-        }
-    }
-    __syncthreads();
-
-    // ---- exclusive scan of the cell counts (9 per thread) ------------------------
-    {
-        constexpr int PER = BRICK_CELLS / DEP_THREADS;
-        static_assert(PER * DEP_THREADS == BRICK_CELLS, "cells must divide evenly among the threads");
-        int v[PER], s = 0;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) { v[k] = cnt[tid * PER + k]; s += v[k]; }
-        int incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            int w = lane < DEP_THREADS / 32 ? wsum[lane] : 0;
-            int wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            wsum[32 + lane] = wi - w;   // exclusive warp offsets
-        }
-        __syncthreads();
-        int run = wsum[32 + warp] + incl - s;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) { cnt[tid * PER + k] = run; run += v[k]; }
-        if (tid == DEP_THREADS - 1) cnt[BRICK_CELLS] = run;
-    }
-    __syncthreads();
-
-    // ---- scatter into cell order --------------------------------------------------
-#pragma unroll
-    for (int h = 0; h < NBATCH; ++h) {
-        VT v[BATCH];
-#pragma unroll
-        for (int k = 0; k < BATCH; ++k) {
-            const int i = (h * BATCH + k) * DEP_THREADS + tid;
-            v[k] = vals[c0 + min(i, nchunk - 1)];
-        }
-#pragma unroll
-        for (int k = 0; k < BATCH; ++k) {
-            const int pk = packed[h * BATCH + k];
-            if (pk >= 0) {
-                unpack_pair(v[k], sel);
-                const int slot = cnt[pk & 8191] + (pk >> 13);
-                sx[slot] = v[k].x; sy[slot] = v[k].y; sz[slot] = v[k].z;
-                if constexpr (MASS) sm[slot] = v[k].m;
-            }
-        }
-    }
-    __syncthreads();
-}
-
-template <int S, bool MASS, typename VT>
-__global__ void __launch_bounds__(DEP_THREADS, DEP_CTAS_PER_SM)
-brick_deposit_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
-                     const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
-                     DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int *cnt = reinterpret_cast<int *>(smem_raw);                 // [BRICK_CELLS + 1]
-    int *wsum = cnt + BRICK_CELLS + 1;                            // [64] scan scratch
-    float *sx = reinterpret_cast<float *>(wsum + 64);
-    float *sy = sx + CH;
-    float *sz = sy + CH;
-    float *sm = sz + CH;                                          // only if MASS
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    constexpr int OFF = (S == 3) ? 1 : 0;   // window origin = home cell - OFF
-    constexpr int W = 3 + S - 1;            // edge of a warp's private window: its 3 columns + halo
-    // this warp's 3 x 3 block of (x,y) columns inside the brick
-    const int bi = warp / (BY / 3), bj = warp % (BY / 3);
-
-    const unsigned int nfilled = *nfilled_ptr;
-    // One CTA per non-empty brick, in list order (x-major: neighbouring windows meet in L2).  CTAs retire
-    // all the time, so kernels of a higher-priority stream (the slab path's FFT / transpose of the first mesh)
-    // get SMs while this one runs; a persistent grid would hold every register file until it ends.
-    for (unsigned int slot = blockIdx.x; slot < nfilled; slot += gridDim.x) {
-        if (slot != blockIdx.x) __syncthreads();
-        const unsigned int brick = filled[slot];
-        const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
-
-        const int bz = brick % B.nbz;
-        const int by = (brick / B.nbz) % B.nby;
-        const int bx = brick / (B.nbz * B.nby);
-
-        for (unsigned int c0 = pbeg; c0 < pend; c0 += CH) {
-            const int nchunk = (int)min((unsigned int)CH, pend - c0);
-            if (c0 != pbeg) __syncthreads();   // every warp is done with the previous chunk's lists
-            sort_chunk_by_cell<S, MASS, VT, CH>(vals, c0, nchunk, sel, cnt, wsum, sx, sy, sz, sm);
-
-            // ---- moments per home cell; each warp walks its own 9 columns, no CTA barrier ----
-            // lane = z-cell of the column (home z + OFF), so the z-spread is two shuffles: every lane
-            // gets the middle weight of its own home cell plus the outer weights of its z-neighbours
-            // (halo lanes have no home cell; CIC: lane 0 must drop its wrapped-around 'up').  The
-            // (x,y)-spread is a register add into the warp's window, static indices throughout.
-            //      The window (one z-cell per lane) lives in registers during this phase only, so that it
-            //      does not add to the register pressure of the sort phases above.  (A rolled loop over i
-            //      with a sliding window of S planes has a third of the code and measured 3 % slower.)
-            float R[W][W];
-#pragma unroll
-            for (int u = 0; u < W; ++u)
-#pragma unroll
-                for (int v = 0; v < W; ++v) R[u][v] = 0.f;
-            const float up_on = (S == 2 && lane == 0) ? 0.f : 1.f;
-            const float fz = (float)(lane - OFF);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) {
-#pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const int cx = 3 * bi + i, cy = 3 * bj + j;
-                    const int cell = (cx * BY + cy) * BZ + lane;
-                    const int beg = cnt[cell], end = cnt[cell + 1];
-                    if (__ballot_sync(0xffffffffu, end > beg) == 0u) continue;
-                    Moments<S, MASS> M;
-                    const float fx = (float)cx, fy = (float)cy;
-                    {
-                        const bool any = end > beg;
-                        const int p = any ? beg : 0;
-                        M.init(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? (any ? sm[p] : 0.f) : 1.f, any);
-                    }
-                    for (int p = beg + 1; p < end; ++p)
-                        M.add(sx[p] - fx, sy[p] - fy, sz[p] - fz, MASS ? sm[p] : 1.f);
-#pragma unroll
-                    for (int a = 0; a < S; ++a)
-#pragma unroll
-                        for (int b = 0; b < S; ++b) {
-                            const float up = __shfl_up_sync(0xffffffffu, M.get(a, b, S - 1), 1);
-                            float own;
-                            if (S == 2) {
-                                own = fmaf(up, up_on, M.get(a, b, 0));
-                            } else {
-                                const float dn = __shfl_down_sync(0xffffffffu, M.get(a, b, 0), 1);
-                                own = M.get(a, b, S / 2) + up + dn;
-                            }
-                            R[i + a][j + b] += own;
-                        }
-                }
-            }
-
-            // ---- add the warp's window to the mesh: one coalesced 128-byte RED per (x,y) column ----
-            const int gz = wrap_index32(bz * BrickZ<S>::CELLS - OFF + lane, G.N);
-            const int x0 = bx * BX + 3 * bi - OFF, y0 = by * BY + 3 * bj - OFF;
-            int row[W];                 // offset of (y0 + v, gz) inside a plane: < N * ldz, fits 32 bits
-#pragma unroll
-            for (int v = 0; v < W; ++v) row[v] = wrap_index32(y0 + v, G.N) * G.ldz + gz;
-#pragma unroll
-            for (int u = 0; u < W; ++u) {
-                int px = x0 + u;
-                bool ok = true;
-                if (G.slab) ok = px >= 0 && px < G.nplanes;
-                else px = wrap_index32(px, G.N);
-                float *plane = mesh + (long long)px * G.N * G.ldz;
-#pragma unroll
-                for (int v = 0; v < W; ++v)
-                    if (ok && R[u][v] != 0.f) atomicAdd(plane + row[v], R[u][v]);
-            }
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// Particle-parallel tile kernel (unit masses): one THREAD per particle, the brick's window of the mesh lives in shared
-// memory as 32-bit FIXED-POINT integers and every one of the S^3 weights goes there with a native integer ATOMS.ADD
-// (shared-memory float atomics are CAS loops on sm_100; integer adds are not).  No in-brick sort, no per-cell loop:
-// all 32 lanes work on every instruction, whatever the cell occupancy.
-//   Quantum 2^-s of a particle's mass, s chosen PER CHUNK of <= PP_FLUSH particles as large as 32 bits allow if every
-//   particle of the chunk put its largest possible weight (1 for CIC, 0.75^3 for TSC) into one cell: s = 22 for the
-//   ~2200 particles of a brick at one particle per cell (TSC), 20..21 for a full chunk, 22 / 23 for sparse bricks.
-//   A weight is rounded to the quantum by ONE FFMA against a magic constant (1.5 * 2^(23 - s): the sum lands in a
-//   binade whose ulp is the quantum, so the low mantissa bits ARE the fixed-point value).  Integer adds commute: a
-//   brick's contribution to the mesh does not depend on the order in which the partition filed its particles.
-//   The tile goes to the mesh as before: one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
-constexpr int PP_FLUSH = 4095;                        // particles between two flushes
-constexpr int PP_THREADS = 256;
-#ifndef APK_PP_CTAS
-#define APK_PP_CTAS 6
+// Tile kernel: one CTA per brick, one THREAD per particle.  The brick's window of the mesh lives in shared memory as
+// 32-bit FIXED-POINT integers and every one of the S^3 weights goes there with a native integer ATOMS.ADD (measured on
+// B200, tools/ubench/atoms.cu: 0.7 cycles per warp-instruction and SM without bank conflicts, 1.9 with random cells;
+// the float atomicAdd is a CAS loop at 3.5 - 9.6).  No in-brick sort, no per-cell loop: all 32 lanes work on every
+// instruction, whatever the cell occupancy.
+//   Quantum: 2^-s of the largest |mass| in the chunk (1 for unit masses), s chosen PER CHUNK of <= TILE_FLUSH particles
+//   as large as 32 bits allow if every particle of the chunk put its largest possible weight (1 for CIC, 0.75^3 for
+//   TSC) into one cell: s = 22 for the ~2200 particles of a brick at one particle per cell (TSC), 20 - 21 for a full
+//   chunk, up to 23 for sparse bricks.  A weight is rounded to the quantum by ONE FFMA against a magic constant
+//   (1.5 * 2^(23 - s): the sum lands in a binade whose ulp is the quantum, so the low mantissa bits ARE the
+//   fixed-point value).  Integer adds commute: a brick's contribution to the mesh does not depend on the order in
+//   which the partition filed its particles.
+//   The tile goes to the mesh as one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
+constexpr int TILE_FLUSH = 4095;                      // particles between two flushes of the tile
+constexpr int TILE_THREADS = 256;
+#ifndef APK_TILE_CTAS
+#define APK_TILE_CTAS 6
 #endif
 
-// fractional bits for a chunk of n particles: n * wmax * 2^s < 2^32, s <= SMAX (the magic-constant trick needs
-// wmax <= 2^(22 - s))
+template <int S> struct Tile {
+    static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
+    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ;
+    static constexpr int CELLS = TX * TY * TZ;
+};
+
+// fractional bits for a chunk of n unit-mass particles: n * wmax * 2^s < 2^32, s <= SMAX (the magic-constant trick
+// needs wmax <= 2^(22 - s))
 template <int S>
-__device__ __forceinline__ int pp_frac_bits(int n) {
+__device__ __forceinline__ int tile_frac_bits(int n) {
     constexpr float WMAX = (S == 3) ? 0.43f : 1.001f;          // 0.75^3 = 0.4219 / 1, padded for the rounding
     constexpr int SMAX = (S == 3) ? 23 : 22;
     const float room = (4294967296.f / WMAX) / (float)n;
@@ -534,16 +251,10 @@ __device__ __forceinline__ int pp_frac_bits(int n) {
     return min(s, SMAX);
 }
 
-template <int S> struct PPTile {
-    static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
-    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ;
-    static constexpr int CELLS = TX * TY * TZ;
-};
-
 // nearest brick-local home cell of coordinate l on one axis (clamped to the brick) as float and int, and the offset
 // d = l - home: [-0.5, 0.5] for TSC, [0, 1] for CIC (ties land on either side; the windows are continuous there)
 template <int S>
-__device__ __forceinline__ void pp_home(float l, float last, float &d, int &h) {
+__device__ __forceinline__ void tile_home(float l, float last, float &d, int &h) {
     const float M = 12582912.f;                       // 1.5 * 2^23: adding it rounds to the nearest integer
     float t = (S == 2 ? l - 0.5f : l) + M;
     t = fminf(fmaxf(t, M), M + last);
@@ -551,16 +262,20 @@ __device__ __forceinline__ void pp_home(float l, float last, float &d, int &h) {
     d = l - (t - M);
 }
 
-template <int S, typename VT>
-__global__ void __launch_bounds__(PP_THREADS, APK_PP_CTAS)
-brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
-                        const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
-                        DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
-    using T = PPTile<S>;
+template <int S, bool MASS, typename VT>
+__global__ void __launch_bounds__(TILE_THREADS, APK_TILE_CTAS)
+brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
+                  const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
+                  DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
+    using T = Tile<S>;
     __shared__ unsigned int tile[T::CELLS];
+    __shared__ float red_s[2 * (TILE_THREADS / 32)];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned int nfilled = *nfilled_ptr;
 
+    // One CTA per non-empty brick, in list order (x-major: neighbouring windows meet in L2).  CTAs retire all the
+    // time, so kernels of a higher-priority stream (the slab path's FFT / transpose of the first mesh) get SMs while
+    // this one runs.
+    const unsigned int nfilled = *nfilled_ptr;
     for (unsigned int slot = blockIdx.x; slot < nfilled; slot += gridDim.x) {
         const unsigned int brick = filled[slot];
         const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
@@ -568,28 +283,66 @@ brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restr
         const int by = (brick / B.nbz) % B.nby;
         const int bx = brick / (B.nbz * B.nby);
 
-        for (int i = tid; i < T::CELLS; i += PP_THREADS) tile[i] = 0u;
+        __syncthreads();                              // (persistent grids) the previous brick's flush is complete
+        for (int i = tid; i < T::CELLS; i += TILE_THREADS) tile[i] = 0u;
         __syncthreads();
 
-        for (unsigned int c0 = pbeg; c0 < pend; c0 += PP_FLUSH) {
-            const unsigned int c1 = min(c0 + (unsigned int)PP_FLUSH, pend);
-            const int frac_bits = pp_frac_bits<S>((int)(c1 - c0));
-            const unsigned int magic_bits = ((unsigned int)(127 + 23 - frac_bits) << 23) | 0x400000u;   // 1.5 * 2^(23 - s)
+        for (unsigned int c0 = pbeg; c0 < pend; c0 += TILE_FLUSH) {
+            const unsigned int c1 = min(c0 + (unsigned int)TILE_FLUSH, pend);
+            // ---- masses: unit = the power of two at or above the chunk's largest |mass| (scaling by it is exact), and
+            //      the fixed-point scale from the chunk's sum of |mass|: no cell can overflow 31 bits + sign even if
+            //      every particle put its largest weight into it.  The conversion is FMUL + F2I here (the magic-constant
+            //      trick would cap the scale at 2^22 / unit, too coarse when the masses span decades).
+            float unit = 1.f, inv_unit = 1.f, mscale = 1.f;
+            int frac_bits = 0;
+            if constexpr (MASS) {
+                float top = 0.f, sum = 0.f;
+                for (unsigned int p = c0 + tid; p < c1; p += TILE_THREADS) {
+                    const float a = fabsf(vals[p].m);
+                    top = fmaxf(top, a);
+                    sum += a;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                }
+                if (lane == 0) { red_s[warp] = top; red_s[TILE_THREADS / 32 + warp] = sum; }
+                __syncthreads();
+                top = red_s[0]; sum = red_s[TILE_THREADS / 32];
+#pragma unroll
+                for (int i = 1; i < TILE_THREADS / 32; ++i) { top = fmaxf(top, red_s[i]); sum += red_s[TILE_THREADS / 32 + i]; }
+                // 2^ceil(log2(top)), clamped to normal numbers whose reciprocal is normal too
+                int e = ((__float_as_int(top) >> 23) & 0xff) + ((__float_as_int(top) & 0x7fffff) ? 1 : 0);
+                e = min(max(e, 2), 252);
+                unit = __int_as_float(e << 23);
+                inv_unit = __int_as_float((254 - e) << 23);
+                if (!(top > 0.f) || !(sum < 3.0e38f)) { unit = 1.f; inv_unit = 0.f; sum = 1.f; }   // all-zero, inf or NaN masses: nothing to add
+                constexpr float WMAX = (S == 3) ? 0.43f : 1.001f;
+                const float room = 2147483648.f / (WMAX * fmaxf(sum * inv_unit, 1.f));          // sum |m'| <= n, >= 1 when top > 0
+                frac_bits = min(((__float_as_int(room) >> 23) & 0xff) - 127, 30);
+                mscale = __int_as_float((127 + frac_bits) << 23);
+            } else {
+                frac_bits = tile_frac_bits<S>((int)(c1 - c0));
+            }
+            const unsigned int magic_bits = ((unsigned int)(127 + 23 - (MASS ? 0 : frac_bits)) << 23) | 0x400000u;   // 1.5 * 2^(23 - s)
             const float magic = __int_as_float((int)magic_bits);
-            const float quantum = __int_as_float((127 - frac_bits) << 23);                                // 2^-s
+            const float quantum = __int_as_float((127 - frac_bits) << 23) * unit;                         // 2^-s mass units
+
             // ---- one thread per particle; the next particle's loads are in flight while this one is deposited ----
             unsigned int p = c0 + tid;
             VT nxt = {};
             if (p < c1) nxt = vals[p];
-            for (; p < c1; p += PP_THREADS) {
+            for (; p < c1; p += TILE_THREADS) {
                 VT v = nxt;
-                if (p + PP_THREADS < c1) nxt = vals[p + PP_THREADS];
+                const unsigned int q = p + TILE_THREADS;
+                if (q < c1) nxt = vals[q];
                 if (!unpack_pair(v, sel)) continue;
                 float dx, dy, dz;
                 int hx, hy, hz;
-                pp_home<S>(v.x, (float)(BX - 1), dx, hx);
-                pp_home<S>(v.y, (float)(BY - 1), dy, hy);
-                pp_home<S>(v.z, (float)(BrickZ<S>::CELLS - 1), dz, hz);
+                tile_home<S>(v.x, (float)(BX - 1), dx, hx);
+                tile_home<S>(v.y, (float)(BY - 1), dy, hy);
+                tile_home<S>(v.z, (float)(BrickZ<S>::CELLS - 1), dz, hz);
                 float wx[S], wy[S], wz[S];
                 if (S == 2) {
                     wx[0] = 1.f - dx; wx[S - 1] = dx; wy[0] = 1.f - dy; wy[S - 1] = dy; wz[0] = 1.f - dz; wz[S - 1] = dz;
@@ -599,6 +352,11 @@ brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restr
                     wy[0] = 0.5f * ay * ay; wy[S / 2] = fmaf(-dy, dy, 0.75f); wy[S - 1] = 0.5f * cy * cy;
                     wz[0] = 0.5f * az * az; wz[S / 2] = fmaf(-dz, dz, 0.75f); wz[S - 1] = 0.5f * cz * cz;
                 }
+                if constexpr (MASS) {
+                    const float m = (v.m * inv_unit) * mscale;                   // |m / unit| <= 1, exact; times 2^s
+#pragma unroll
+                    for (int a = 0; a < S; ++a) wx[a] *= m;
+                }
                 unsigned int *cell = tile + (hx * T::TY + hy) * T::TZ + hz;     // window origin (home - OFF) in tile coordinates
 #pragma unroll
                 for (int a = 0; a < S; ++a)
@@ -607,8 +365,9 @@ brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restr
                         const float wxy = wx[a] * wy[b];
 #pragma unroll
                         for (int c = 0; c < S; ++c) {
-                            const unsigned int q = (unsigned int)__float_as_int(fmaf(wxy, wz[c], magic)) - magic_bits;
-                            atomicAdd(cell + (a * T::TY + b) * T::TZ + c, q);
+                            const unsigned int fx = MASS ? (unsigned int)__float2int_rn(wxy * wz[c])
+                                                         : (unsigned int)__float_as_int(fmaf(wxy, wz[c], magic)) - magic_bits;
+                            atomicAdd(cell + (a * T::TY + b) * T::TZ + c, fx);
                         }
                     }
             }
@@ -617,16 +376,18 @@ brick_deposit_pp_kernel(const VT *__restrict__ vals, const unsigned int *__restr
             // ---- tile -> mesh: one coalesced 128-byte RED per (x,y) column, zeros skipped; the tile is cleared on the way ----
             const int gz = wrap_index32(bz * BrickZ<S>::CELLS - T::OFF + lane, G.N);
             const int x0 = bx * BX - T::OFF, y0 = by * BY - T::OFF;
-            for (int col = warp; col < T::TX * T::TY; col += PP_THREADS / 32) {
+            for (int col = warp; col < T::TX * T::TY; col += TILE_THREADS / 32) {
                 const int u = col / T::TY, w = col - u * T::TY;
-                const unsigned int q = tile[col * T::TZ + lane];
+                const unsigned int fx = tile[col * T::TZ + lane];
                 if (c1 < pend) tile[col * T::TZ + lane] = 0u;
                 int px = x0 + u;
                 bool ok = true;
                 if (G.slab) ok = px >= 0 && px < G.nplanes;
                 else px = wrap_index32(px, G.N);
-                if (ok && q != 0u)
-                    atomicAdd(mesh + ((long long)px * G.N + wrap_index32(y0 + w, G.N)) * G.ldz + gz, (float)q * quantum);
+                if (ok && fx != 0u) {
+                    const float val = MASS ? (float)(int)fx * quantum : (float)fx * quantum;
+                    atomicAdd(mesh + ((long long)px * G.N + wrap_index32(y0 + w, G.N)) * G.ldz + gz, val);
+                }
             }
             __syncthreads();
         }
@@ -658,10 +419,11 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
         if (G.t32 >= 0.f) G1.t32 = G.t32 + 0.5f;
     }
     const size_t need = deposit_sorted_workspace_bytes(P, np, MASS, PAIR);
-    APK_REQUIRE(!PAIR || 2 * np < 0xffffffffLL, "apk_deposit_interlaced: more than 2^31 particles on one device");
-    APK_REQUIRE(P->workspace && P->workspace_bytes >= need,
-                "apk_deposit: sorted path needs %zu workspace bytes, %zu set (apk_plan_workspace_bytes / apk_plan_set_workspace)",
-                need, P->workspace_bytes);
+    APK_REQUIRE(!PAIR || 2 * np < 0xffffffffLL, "apk_deposit_interlaced: more than 2^31 - 1 particles on one device");
+    // the cuFFT work areas live in the last fft_work_bytes of the same workspace and may be in use on another stream
+    APK_REQUIRE(P->workspace && P->workspace_bytes >= need + P->fft_work_bytes + 256,
+                "apk_deposit: sorted path needs %zu workspace bytes (+ %zu of cuFFT work area), %zu set "
+                "(apk_plan_workspace_bytes / apk_plan_set_workspace)", need, P->fft_work_bytes + 256, P->workspace_bytes);
     APK_REQUIRE(np < 0xffffffffLL, "apk_deposit: more than 2^32-1 particles on one device");
     unsigned char *w = (unsigned char *)P->workspace;
     VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np * (PAIR ? 2 : 1));
@@ -691,32 +453,16 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
         (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, G1, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
 
-    // unit masses: particle-parallel fixed-point tile kernel; with masses: the per-cell register-moment kernel
-    static const bool force_cell = [] { const char *e = getenv("APK_TILE_KERNEL"); return e && !strcmp(e, "cell"); }();
-    const int ctas = B.nbricks;     // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
+    // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
+    const int ctas = B.nbricks;
+    auto kern = brick_tile_kernel<S, MASS, VT>;
     P->mark(3, st);
-    if (!MASS && !force_cell) {
-        if constexpr (!MASS) {
-            auto kern = brick_deposit_pp_kernel<S, VT>;
-            kern<<<ctas, PP_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, PAIR ? 0 : -1);
-            APK_CUDA(cudaGetLastError());
-            if (PAIR) {
-                if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
-                kern<<<ctas, PP_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G1, B, mesh1, 1);
-                APK_CUDA(cudaGetLastError());
-            }
-        }
-    } else {
-        auto kern = brick_deposit_kernel<S, MASS, VT>;
-        const size_t smem = DepSmem<MASS>::bytes;
-        APK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, PAIR ? 0 : -1);
+    kern<<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, PAIR ? 0 : -1);
+    APK_CUDA(cudaGetLastError());
+    if (PAIR) {
+        if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
+        kern<<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G1, B, mesh1, 1);
         APK_CUDA(cudaGetLastError());
-        if (PAIR) {
-            if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
-            kern<<<ctas, DEP_THREADS, smem, st>>>(vals, brick_start, filled, counter + 1, G1, B, mesh1, 1);
-            APK_CUDA(cudaGetLastError());
-        }
     }
     P->mark(4, st);
     if (P->timing) { P->dep_timed = true; P->dep_sorted = true; }

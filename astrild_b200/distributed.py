@@ -52,30 +52,36 @@ class CudaSlabBackend:
         (positions (n,3), masses or None, per-destination counts).  Everything else stays put."""
         return self.route_end(self.route_begin(pos, mass, pos_scale))
 
-    def route_begin(self, pos, mass, pos_scale: float, capacity: int | None = None) -> dict:
-        """Launches the routing kernels on the current stream and returns without waiting for them."""
+    def route_begin(self, pos, mass, pos_scale: float, capacity: int | None = None, counts=None) -> dict:
+        """Launches the routing kernels on the current stream and returns without waiting for them.
+        counts: int64[2 * nranks] device tensor that receives the per-destination counts (default: the backend's own)."""
         eng = self.eng
         p0, p1, p2, layout, dt, npart, keep = eng._positions(pos)
         m = None
-        if mass is not None:
+        if mass is not None and not np.isscalar(mass):          # a scalar weight is the caller's to apply (SlabPk.power)
             m = eng._to_device(mass).to(dt).contiguous()
         code = _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64
         if capacity is None:
             capacity = min(max(npart, 1), max(1 << 16, npart // 8))
-        eng.ensure_workspace(max(npart, capacity), m is not None)   # the leavers are staged in the plan workspace
+        # the leavers are staged in the plan workspace: capacity * (3 + [mass]) * itemsize + 64 bytes; the workspace holds
+        # at least 12 bytes per particle it is sized for
+        item = 4 if dt == torch.float32 else 8
+        stage_rows = (capacity * item * (4 if m is not None else 3) + 64 + 11) // 12
+        eng.ensure_workspace(max(npart, stage_rows), m is not None)
         out_pos = torch.empty((capacity, 3), dtype=dt, device=self.device)
         out_mass = torch.empty(capacity, dtype=dt, device=self.device) if m is not None else None
+        cnt = self._counts if counts is None else counts
         _lib.call("apk_route_particles", eng._plan, _ptr(p0), _ptr(p1), _ptr(p2), layout, code, float(pos_scale),
-                  _ptr(m), code, int(npart), self.nranks, _ptr(self._counts), int(capacity), _ptr(out_pos),
+                  _ptr(m), code, int(npart), self.nranks, _ptr(cnt), int(capacity), _ptr(out_pos),
                   _ptr(out_mass), eng.stream)
         return {"pos": pos, "mass": mass, "pos_scale": pos_scale, "capacity": capacity, "out_pos": out_pos,
-                "out_mass": out_mass, "keep": (keep, m)}
+                "out_mass": out_mass, "keep": (keep, m), "counts": cnt}
 
     def route_end(self, h: dict):
         """Reads the per-destination counts (blocks the host on the CURRENT stream, which must be ordered after
         route_begin's) and returns (positions, masses, counts).  More leavers than the staging buffer holds (more
         than 1/8 of the particles change slab: rare) means a second, larger pass after a device synchronise."""
-        counts = self._counts[: self.nranks].cpu().tolist()
+        counts = h["counts"][: self.nranks].cpu().tolist()
         total = int(sum(counts))
         if total > h["capacity"]:
             torch.cuda.synchronize(self.device)       # nothing else may be using the plan workspace
@@ -195,14 +201,14 @@ class CudaSlabBackend:
     def bin(self, binning, c1, c1s) -> torch.Tensor:
         return self.eng.bin_power_raw(binning, c1, c1s)
 
-    def to_reduce_tensor(self, raw, total_mass) -> torch.Tensor:
-        """[ksum | psum_re | psum_im | nmodes as float64 | total mass] for ONE all-reduce."""
+    def to_reduce_tensors(self, raw, total_mass) -> tuple:
+        """([ksum | psum_re | psum_im | total mass] float64, mode counts int64): the two all-reduces of the path.
+        The counts stay integers end to end."""
         nb1 = raw.shape[1]
-        out = torch.empty(4 * nb1 + 1, dtype=torch.float64, device=self.device)
+        out = torch.empty(3 * nb1 + 1, dtype=torch.float64, device=self.device)
         out[: 3 * nb1] = raw[:3].reshape(-1)
-        out[3 * nb1: 4 * nb1] = raw[3].view(torch.int64).to(torch.float64)      # exact below 2^53
-        out[4 * nb1] = total_mass[0]
-        return out
+        out[3 * nb1] = total_mass[0]
+        return out, raw[3].view(torch.int64).clone()
 
 
 class TorchDistComm:
@@ -280,6 +286,8 @@ class SlabPk:
         self.eng = getattr(backend, "eng", None)
         self.ghost_lo, self.ghost_hi = 1, 2
         self.profile, self.last_profile = False, {}
+        self.last_info: dict = {}                                 # which transpose ran, its time, the critical stage
+        self.stream_rows = 1 << 24                                # host inputs larger than this are uploaded in chunks
         self.p2p = os.environ.get("APK_SLAB_P2P", "1") != "0"     # fused peer-store transpose (falls back to NCCL)
         if self.P > 1 and self.n0 < 2:
             raise AstrildPkError("each rank needs at least 2 mesh planes")
@@ -342,17 +350,29 @@ class SlabPk:
                 marks.append((name, ev))
 
         mark("start")
+        scalar_mass = 1.0
+        if mass is not None and np.isscalar(mass):   # one weight for all: deposit unit weights, scale at the end
+            scalar_mass, mass = float(mass), None
         eng = getattr(be, "eng", None)
-        if eng is not None:                          # host inputs: ONE upload serves routing and deposit
+        self.last_info = {"transpose": "local" if P == 1 else "nccl-a2a"}
+        self._transpose_events = []
+        if eng is not None:
+            first = pos[0] if isinstance(pos, (tuple, list)) else pos
+            on_host = not (isinstance(first, torch.Tensor) and first.is_cuda)
+            if on_host and P > 1 and not routed and int(first.shape[0]) > self.stream_rows and hasattr(be, "setup_p2p"):
+                # host inputs: chunked upload, each chunk routed and deposited while the next one is in flight
+                grids, total = self._streamed_host(pos, mass, ps, mark)
+                return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark, scalar_mass)
+            # ONE upload serves routing and deposit
             pos = tuple(eng._to_device(c) for c in pos) if isinstance(pos, (tuple, list)) else eng._to_device(pos)
-            if mass is not None and not np.isscalar(mass):
+            if mass is not None:
                 mass = eng._to_device(mass)
         side = getattr(be, "side_stream", None)
         if (P > 1 and self.interlaced and self.p2p and side is not None and torch.cuda.is_available()
                 and isinstance(self.comm, TorchDistComm) and hasattr(be, "setup_p2p")
                 and be.setup_p2p(self.comm.group, 2)):
             grids, total = self._pipelined_pair(pos, mass, ps, routed, mark)
-            return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark)
+            return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark, scalar_mass)
         # 1. route: only particles that change slab travel; the slab deposit ignores particles it
         #    does not own, so the caller's arrays are deposited as they are
         side = getattr(be, "side_stream", None)
@@ -413,14 +433,37 @@ class SlabPk:
             if fp.shape[0]:
                 deposit_into(fp, fm, meshes)
         mark("deposit")
-        owned = self._exchange_ghosts(meshes)
+        grids, total = self._ghosts_fft_transpose(meshes, mark)
         del meshes
+        return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark, scalar_mass)
+
+    def _timed_transpose(self, fn, stream):
+        """Runs fn() between two CUDA events on `stream` (the transposes' own time, for the NVLink roofline)."""
+        if not (self.profile and torch.cuda.is_available()):
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = fn()
+        e1.record(stream)
+        self._transpose_events.append((e0, e1))
+        return out
+
+    def _ghosts_fft_transpose(self, meshes: list, mark) -> tuple:
+        """Stages 3-6 for complete slab meshes: ghost planes, 2-D r2c, x<->y transpose, 1-D c2c.
+        Returns (transposed k-grids [N][ny][Nk], total mass tensor)."""
+        be, P = self.backend, self.P
+        side = getattr(be, "side_stream", None)
+        owned = self._exchange_ghosts(meshes)
         mark("ghosts")
         # 4. 2-D FFT, 5. transpose, 6. 1-D FFT
         #    pipelined per field: while field f is packed and exchanged on a side stream, the 2-D FFT of
         #    field f+1 (and later the 1-D FFT of field f-1) runs on the main stream
         use_p2p = (P > 1 and self.p2p and isinstance(self.comm, TorchDistComm) and hasattr(be, "setup_p2p")
                    and be.setup_p2p(self.comm.group, 2 if self.interlaced else 1))
+        if use_p2p:
+            self.last_info["transpose"] = "p2p-store"
+        elif P > 1 and self.p2p and hasattr(be, "_p2p_error"):
+            self.last_info["transpose_fallback_reason"] = be._p2p_error
         has_dc = hasattr(be, "dc_sum")
         total = None
         if use_p2p and side is not None:
@@ -439,8 +482,7 @@ class SlabPk:
                     side.wait_event(ready)
                     if f == 0:
                         be.p2p_barrier(0)            # every rank is done reading the previous step's buffers
-                    be.transpose_p2p_store(f, g2, side)
-                    be.p2p_barrier(1 + (f & 1))      # field f has landed everywhere
+                    self._timed_transpose(lambda: (be.transpose_p2p_store(f, g2, side), be.p2p_barrier(1 + (f & 1))), side)   # field f has landed everywhere
                     ev = torch.cuda.Event()
                     ev.record(side)
                 landed.append(ev)
@@ -454,7 +496,9 @@ class SlabPk:
             grids = [be.fft2d(o) for o in owned]
             total = be.dc_sum(grids[0]) if has_dc else be.mesh_sum(owned[0])
             mark("fft2d")
-            grids = be.transpose_p2p(grids) if use_p2p else self._transpose(grids)
+            cur = torch.cuda.current_stream(be.device) if torch.cuda.is_available() and hasattr(be, "device") else None
+            grids = self._timed_transpose(lambda: be.transpose_p2p(grids) if use_p2p else self._transpose(grids), cur) \
+                if cur is not None else (be.transpose_p2p(grids) if use_p2p else self._transpose(grids))
             del owned
             mark("transpose")
             grids = [be.fft1d(g, self.ny) for g in grids]
@@ -471,7 +515,7 @@ class SlabPk:
                 o.record_stream(side)
                 with torch.cuda.stream(side):
                     side.wait_event(ready)
-                    t = self._transpose([g2])[0]
+                    t = self._timed_transpose(lambda: self._transpose([g2])[0], side)
                     ev = torch.cuda.Event()
                     ev.record(side)
                 t.record_stream(main)
@@ -483,7 +527,119 @@ class SlabPk:
                 grids.append(be.fft1d(t, self.ny))
             del owned
             mark("fft+transpose")
-        return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark)
+        return grids, total
+
+    def _streamed_host(self, pos, mass, ps: float, mark) -> tuple:
+        """HOST inputs on P > 1 GPUs: the rank's share is uploaded in chunks on a copy stream; every chunk is routed
+        (its leavers staged on the device) and deposited into the slab meshes while the next chunk is in flight, so the
+        end-to-end time is the PCIe time plus the tail (exchange of the leavers, ghosts, FFTs, binning) instead of
+        upload + everything.  Pinned host memory gives asynchronous copies.  Returns (k-grids, total mass tensor)."""
+        be, eng = self.backend, self.backend.eng
+        cols = list(pos) if isinstance(pos, (tuple, list)) else None
+
+        def host_tensor(a):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            return t if t.dtype in (torch.float32, torch.float64) else t.to(torch.float64)
+
+        srcs = [host_tensor(c) for c in cols] if cols is not None else [host_tensor(pos)]
+        if mass is not None:
+            srcs.append(host_tensor(mass).to(srcs[0].dtype))
+        npart, rows = int(srcs[0].shape[0]), self.stream_rows
+        nchunk = (npart + rows - 1) // rows
+        main = torch.cuda.current_stream(be.device)
+        copy_stream = torch.cuda.Stream(be.device)
+        be.prepare_ffts(self.ny)
+        nshift = 2 if self.interlaced else 1
+        meshes = be.zeroed_meshes(nshift)
+        bufs = [[torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=be.device) for t in srcs] for _ in range(2)]
+        copy_stream.wait_stream(main)
+        for pair in bufs:
+            for buf in pair:
+                buf.record_stream(copy_stream)
+        counts = torch.zeros((nchunk, 2 * self.P), dtype=torch.int64, device=be.device)
+        ready, free, staged = [torch.cuda.Event() for _ in range(2)], [None, None], []
+        for c, a in enumerate(range(0, npart, rows)):
+            b, sl = min(a + rows, npart), c & 1
+            with torch.cuda.stream(copy_stream):
+                if free[sl] is not None:
+                    copy_stream.wait_event(free[sl])
+                for buf, src in zip(bufs[sl], srcs):
+                    buf[: b - a].copy_(src[a:b], non_blocking=True)
+                ready[sl].record(copy_stream)
+            main.wait_event(ready[sl])
+            part = [buf[: b - a] for buf in bufs[sl]]
+            ppos = tuple(part[:3]) if cols is not None else part[0]
+            pm = part[-1] if mass is not None else None
+            # every particle of the chunk may leave: a staging buffer of the chunk's size never needs a second pass
+            staged.append(be.route_begin(ppos, pm, ps, capacity=b - a, counts=counts[c]))
+            if self.interlaced:
+                be.deposit_pair(ppos, pm, self.resampler, ps, out=tuple(meshes))
+            else:
+                be.deposit(ppos, pm, self.resampler, 0.0, ps, out=meshes[0])
+            free[sl] = torch.cuda.Event()
+            free[sl].record(main)
+        main.wait_stream(copy_stream)
+        mark("upload+deposit")
+        # the leavers of all chunks, grouped by destination, in ONE all-to-all-v
+        per = counts[:, : self.P].cpu().numpy()                      # [chunk][destination]
+        send_counts = per.sum(axis=0).astype(np.int64).tolist()
+        segs_p, segs_m = [], []
+        for d in range(self.P):
+            for c, h in enumerate(staged):
+                n = int(per[c, d])
+                if n:
+                    o = int(per[c, :d].sum())
+                    segs_p.append(h["out_pos"][o:o + n])
+                    if h["out_mass"] is not None:
+                        segs_m.append(h["out_mass"][o:o + n])
+        like = staged[0]["out_pos"]
+        sp = torch.cat(segs_p) if segs_p else like[:0]
+        sm = (torch.cat(segs_m) if segs_m else staged[0]["out_mass"][:0]) if mass is not None else None
+        del staged
+        fp = self.comm.all_to_all_rows(sp, send_counts, lambda r: be.empty_like_rows(sp, r))
+        fm = self.comm.all_to_all_rows(sm, send_counts, lambda r: be.empty_like_rows(sm, r)) if sm is not None else None
+        if fp.shape[0]:
+            method = "atomic" if fp.shape[0] < (1 << 22) else "auto"
+            if self.interlaced:
+                be.deposit_pair(fp, fm, self.resampler, ps, out=tuple(meshes), method=method, timed=False)
+            else:
+                be.deposit(fp, fm, self.resampler, 0.0, ps, out=meshes[0], method=method)
+        mark("exchange")
+        return self._ghosts_fft_transpose(meshes, mark)
+
+    def routing_stress(self, pos, pos_scale: float, kmin: float, seed: int = 0, steps: int = 2) -> dict:
+        """The all-to-all-v at its design load: the rank's particles are shifted along x by (i mod P) / P, i = index in
+        blocks of 65536, so that (P - 1) / P of them change slab (each rank then holds a 1/P sample of every slab) while
+        the order inside a block stays coherent.  Runs the whole path on that set and returns the step time and the
+        stage split of rank 0's last step; not part of the timed region of bench.py."""
+        P = self.P
+        cols = [c.clone() for c in pos]
+        idx = torch.arange(cols[0].numel(), device=cols[0].device) // 65536
+        shift = (idx % P).to(cols[0].dtype) / P
+        x = cols[0] * (pos_scale if pos_scale != 1.0 else 1.0) + shift
+        cols[0] = ((x - torch.floor(x)) / (pos_scale if pos_scale != 1.0 else 1.0)).clamp_(0, torch.finfo(cols[0].dtype).max)
+        cols[0] = torch.where(cols[0] * pos_scale >= 1.0, torch.zeros_like(cols[0]), cols[0])
+        del idx, shift, x
+        was = self.profile
+        self.profile = True
+        res = None
+        times = []
+        for _ in range(steps):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = self.power(tuple(cols), pos_scale=pos_scale, kmin=kmin, normalize=True)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        self.profile = was
+        t = torch.tensor([times[-1]], dtype=torch.float64, device=cols[0].device)
+        if P > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.comm.group)
+        moved = cols[0].numel() * (P - 1) / P
+        return {"ms_per_step": float(t.item()), "particles_leaving_per_rank": int(moved),
+                "bytes_out_per_gpu": int(moved * 12), "stages_ms_rank0": {k: round(v, 3) for k, v in self.last_profile.items()},
+                "modes0": int(res["modes"][0])}
 
     def _pipelined_pair(self, pos, mass, ps: float, routed: bool, mark):
         """Interlaced twins on P > 1 GPUs with peer-mapped transposes: everything that concerns mesh 0 after its
@@ -493,6 +649,7 @@ class SlabPk:
         Returns (transposed k-grids [N][ny][Nk] of both meshes, total mass tensor)."""
         be = self.backend
         main, side = torch.cuda.current_stream(be.device), be.side_stream
+        self.last_info["transpose"] = "p2p-store"
         be.prepare_ffts(self.ny)                     # plans first: they size the workspace once
         sp = sm = fp = fm = None
         if not routed:
@@ -545,8 +702,7 @@ class SlabPk:
                     total = be.dc_sum(g2)
                     total.record_stream(main)
                     be.p2p_barrier(0)                # every rank is done reading the previous step's buffers
-                be.transpose_p2p_store(f, g2, side)
-                be.p2p_barrier(1 + f)                # field f has landed everywhere
+                self._timed_transpose(lambda: (be.transpose_p2p_store(f, g2, side), be.p2p_barrier(1 + f)), side)   # field f has landed everywhere
                 ev = torch.cuda.Event()
                 ev.record(side)
                 landed.append(ev)
@@ -558,30 +714,38 @@ class SlabPk:
         mark("ghosts+fft+transpose")
         return grids, total
 
-    def _finish(self, grids, total, kmin, dk, kmax, normalize, marks, mark) -> dict:
+    def _finish(self, grids, total, kmin, dk, kmax, normalize, marks, mark, scalar_mass: float = 1.0) -> dict:
         be, P = self.backend, self.P
         # 7. binning on the transposed slab
         comp = (self.resampler, self.interlaced) if self.compensated else None
         binning = be.make_binning(self.y0, self.ny, kmin, dk, kmax, comp, self.interlaced)
         raw = be.bin(binning, grids[0], grids[1] if self.interlaced else None)
         mark("bin")
-        # 8. reduce
-        red = be.to_reduce_tensor(raw, total)
+        # 8. reduce: float64 sums in one all-reduce, the integer mode counts in another
+        red, cnt = be.to_reduce_tensors(raw, total)
         if P > 1:
             red = self.comm.all_reduce_sum(red)
+            cnt = self.comm.all_reduce_sum(cnt)
         host = red.cpu().numpy()
+        nsum = cnt.cpu().numpy().astype(np.int64)
         mark("reduce")
         if marks:
             prof: dict = {}
             for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
                 prof[name] = prof.get(name, 0.0) + e0.elapsed_time(e1)
             self.last_profile = prof
-        nb1 = (len(host) - 1) // 4
+            if prof:
+                self.last_info["critical_path"] = max(prof, key=prof.get)
+        tev = getattr(self, "_transpose_events", None)
+        if tev:
+            self.last_info["transpose_ms"] = float(sum(a.elapsed_time(b) for a, b in tev))
+            self._transpose_events = None
+        nb1 = (len(host) - 1) // 3
         ksum, pre, pim = host[:nb1], host[nb1:2 * nb1], host[2 * nb1:3 * nb1]
-        nsum = np.rint(host[3 * nb1:4 * nb1]).astype(np.int64)
-        W = host[4 * nb1]
+        W = host[3 * nb1] * scalar_mass
         N, L = self.N, self.L
-        field_scale = (N ** 3 / W) if normalize else 1.0 / (L / N) ** 3
+        # the meshes hold unit-weight deposits when the caller's weight is one scalar: it enters here
+        field_scale = (N ** 3 / W) * scalar_mass if normalize else scalar_mass / (L / N) ** 3
         scale = L ** 3 * field_scale ** 2 / float(N) ** 6
         with np.errstate(invalid="ignore", divide="ignore"):
             k = (ksum / nsum)[1:-1]

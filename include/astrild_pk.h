@@ -8,6 +8,7 @@
  *   apk_deposit        pm.paint(pos, mass=, resampler=)           src/astrild/particles/hutils/stats_subfind.py:130-131
  *   apk_load_mesh      ArrayMesh(value_map, BoxSize=, ...)         src/astrild/power_spectra/power_spectrum_3d.py:183-188, 197-212
  *   apk_fft_r2c        FFTPower -> mesh.compute('complex') (r2c)  src/astrild/power_spectra/power_spectrum_3d.py:189-195
+ *   apk_power_from_particles / apk_power_from_mesh   the two call sites' numerical bodies in one call (see below)
  *   apk_bin_power      FFTPower(mode="1d", kmin=) binning         src/astrild/power_spectra/power_spectrum_3d.py:189-195, 216-222;
  *                                                                  src/astrild/particles/hutils/stats_subfind.py:142-148
  *
@@ -67,8 +68,8 @@ int apk_plan_ghost_planes(const apk_plan *plan, int *n_lo, int *n_hi);
 /* ---- per-kernel timing (CUDA events recorded inside the library, on the caller's stream) ---- */
 /* on != 0: apk_deposit / apk_bin_power bracket their kernels with events.                     */
 int apk_plan_enable_timing(apk_plan *plan, int on);
-/* last apk_deposit on this plan, ms: [0] brick count kernel, [1] brick scan, [2] brick scatter,
- * [3] brick deposit kernel (sorted path) or the atomic kernel.  Synchronises on the last event. */
+/* last apk_deposit on this plan, ms: [0] count pass (0 with the one-pass partition), [1] clearing the cursors and
+ * page table, [2] brick partition kernel, [3] tile kernel(s) (sorted path) or the atomic kernel.  Synchronises on the last event. */
 int apk_plan_last_deposit_ms(apk_plan *plan, float ms[4]);
 /* last apk_bin_power on this binning, ms: [0] fused binning kernel, [1] fold of per-CTA copies  */
 int apk_binning_last_ms(apk_binning *binning, float ms[2]);
@@ -174,6 +175,45 @@ int apk_binning_destroy(apk_binning *binning);
 int apk_bin_power(apk_binning *binning, const void *c1, const void *c1s, const void *c2,
                   const void *c2s, double *ksum, double *psum_re, double *psum_im,
                   int64_t *nmodes, void *stream);
+
+/* ---- binning tables (host side of FFTPower: who decides which float lands on which side of an edge) ---- */
+/* The per-axis tables and edges apk_binning_create takes, computed INSIDE the library with the reference stack's
+ * expression order (pmesh ParticleMesh k tables: w = n * (2 pi / N), k = w * N / L; nbodykit FFTPower:
+ * dk = 2 pi / L, kmax = pi N / L + dk/2, numpy.arange(kmin, kmax, dk); Compensate{CIC,TSC}[Shotnoise]; the interlacing
+ * phase 0.5 k H), so that a C / Fortran caller gets bit-identical bins without re-implementing them.
+ * Call sites: src/astrild/power_spectra/power_spectrum_3d.py:181-195; src/astrild/particles/hutils/stats_subfind.py:142-148.
+ * All outputs are HOST arrays.  k_dtype: APK_F64 (default reading) or APK_F32 (float32 index ramp).
+ * dk <= 0: 2 pi / L;  kmax <= 0: pi N / L + dk / 2.                                                                  */
+int apk_tables_k_axis(int nmesh, double boxsize, int k_dtype, double *k_host /* [nmesh] */);
+int apk_tables_k_edges(int nmesh, double boxsize, double kmin, double dk, double kmax,
+                       double *edges_host /* [capacity] or NULL */, int capacity, int *nedges);
+int apk_tables_hermitian_weights(int nmesh, double *w_host /* [nmesh/2+1] */);
+int apk_tables_compensation(int resampler, int interlaced, int nmesh, double *comp_host /* [nmesh] */);
+int apk_tables_interlace_phase(int nmesh, double boxsize, double *phase_host /* [nmesh] */);
+
+/* ---- one call: particles or gridded fields -> (k, P(k), Nmodes) ------------------------------------------- */
+/* floats of scratch the two calls below need: mesh_elems * (interlaced ? 2 : 1) * nfields                       */
+int apk_power_scratch_elems(const apk_plan *plan, int interlaced, int nfields, int64_t *elems);
+/* SubFind.power_spectrum's numerical body (src/astrild/particles/hutils/stats_subfind.py:129-150: paint -> / dx^3 ->
+ * ArrayMesh -> FFTPower(mode="1d", kmin=) -> power.real) with nbodykit's CatalogMesh options: deposit (interlaced twin
+ * if asked), r2c, fused binning.  normalize = 0 keeps rho = mass / dx^3 (astrild as written), 1 gives 1 + delta.
+ * Particle arguments as in apk_deposit (DEVICE pointers); scratch: DEVICE, apk_power_scratch_elems(plan, interlaced, 1)
+ * floats; the plan's workspace must be set (apk_plan_workspace_bytes).  k_host / power_host / modes_host: HOST arrays
+ * of `capacity` >= nbins entries (nbins = nedges - 1; empty bins give NaN k and power, like nbodykit); total_mass
+ * (may be NULL) receives sum(mass).  The shot noise astrild subtracts is 0 (ArrayMesh); V * sum(m^2) / sum(m)^2 is the
+ * caller's to subtract if wanted.  Synchronises `stream`.  Single-GPU plans only.                                 */
+int apk_power_from_particles(apk_plan *plan, const void *p0, const void *p1, const void *p2, int layout, int pos_dtype,
+                             double pos_scale, const void *mass, int mass_dtype, int64_t np, int resampler,
+                             int interlaced, int compensated, int normalize, double kmin, double dk, double kmax,
+                             float *scratch, double *k_host, double *power_host, int64_t *modes_host, int capacity,
+                             int *nbins, double *total_mass, void *stream);
+/* PowerSpectrum3D._power_spectrum_3d (src/astrild/power_spectra/power_spectrum_3d.py:164-226): value_map1 (and
+ * value_map2 for the cross spectrum Re(c1 conj c2), else NULL): DEVICE, contiguous [N][N][N] of dtype.  ArrayMesh
+ * semantics: no window, no interlacing, no normalisation, shot noise 0.  scratch: apk_power_scratch_elems(plan, 0,
+ * value_map2 ? 2 : 1) floats.                                                                                      */
+int apk_power_from_mesh(apk_plan *plan, const void *value_map1, const void *value_map2, int dtype, double kmin,
+                        double dk, double kmax, float *scratch, double *k_host, double *power_host,
+                        int64_t *modes_host, int capacity, int *nbins, void *stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,6 @@ CSRC = os.path.join(ROOT, "astrild_b200", "csrc")
 OUT_DIR = os.path.join(HERE, "_build")
 SO = os.path.join(OUT_DIR, "libapk_simt.so")
 HOST_PART_MARK = "static size_t max_bricks(const apk_plan *P) {"
-PAGED_HOST_PART_MARK = "static size_t paged_max_bricks(const apk_plan *P) {"
 DYN_SMEM_DECL = "extern __shared__ __align__(16) unsigned char smem_raw[];"
 
 
@@ -20,10 +19,6 @@ def device_part(path: str, mark: str = HOST_PART_MARK) -> str:
     cut = text.index(mark)
     text = text[:cut] + "\n}  // namespace apk\n"
     return text.replace(DYN_SMEM_DECL, "unsigned char *smem_raw = simt::dyn_smem;")
-
-
-def paged_device_part() -> str:
-    return device_part(os.path.join(CSRC, "deposit_paged.cu"), PAGED_HOST_PART_MARK)
 
 
 HOST_MARKS = ("<<<", "APK_CUDA(", "APK_REQUIRE(", "APK_CUFFT(", "set_error(")
@@ -101,14 +96,11 @@ def _gxx(src: str, inc_dir: str, so: str, extra_flags=()) -> str:
     return so
 
 
-def compile_kernels(kernel_text: str, out_dir: str, extra_flags=(), paged_text: str | None = None) -> str:
-    """g++ build of deposit_host.cpp around the given device sources (two-pass partition file, paged file)
-    -> <out_dir>/libapk_simt.so"""
+def compile_kernels(kernel_text: str, out_dir: str, extra_flags=()) -> str:
+    """g++ build of deposit_host.cpp around the given device source -> <out_dir>/libapk_simt.so"""
     os.makedirs(out_dir, exist_ok=True)
     with open(os.path.join(out_dir, "deposit_sorted_kernels.inc"), "w") as f:
         f.write(kernel_text)
-    with open(os.path.join(out_dir, "deposit_paged_kernels.inc"), "w") as f:
-        f.write(paged_device_part() if paged_text is None else paged_text)
     return _gxx("deposit_host.cpp", out_dir, os.path.join(out_dir, "libapk_simt.so"), extra_flags)
 
 
@@ -117,7 +109,7 @@ def _fresh(so: str, srcs) -> bool:
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("deposit_sorted.cu", "deposit_paged.cu", "brick_common.cuh", "apk_common.cuh", "deposit_common.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("deposit_sorted.cu", "brick_common.cuh", "apk_common.cuh", "deposit_common.cuh")]
     srcs += [os.path.join(HERE, f) for f in ("simt.h", "deposit_host.cpp", "build_simt.py")]
     if not force and _fresh(SO, srcs):
         return SO

@@ -3,7 +3,6 @@
 // deposit_sorted_kernels.inc is produced by tests/simt/build_simt.py from the .cu (device part, unchanged).
 #include "simt.h"
 #include "deposit_sorted_kernels.inc"
-#include "deposit_paged_kernels.inc"
 
 #include <algorithm>
 #include <cmath>
@@ -15,40 +14,6 @@ using namespace apk;
 
 namespace {
 
-int g_force_cell_kernel = 0;     // simt_force_cell_kernel(1): unit masses through the per-cell kernel too
-int g_two_pass = 0;              // simt_two_pass(1): the two-pass partition (count, scan, scatter) instead of the paged one
-
-// launch sequence of run_paged(): clear cursors / page table -> one-pass partition -> one tile kernel per mesh
-template <int S, typename PT, bool SOA, bool MASS, bool PAIR>
-void run_paged_host(const void *p0, const void *p1, const void *p2, const void *mass, int mass_f64, long long np,
-                    const DepositGeom &G, float *mesh, float *mesh1, int num_sms) {
-    using VT = typename std::conditional<MASS, P4, P3>::type;
-    const BrickGrid B = make_brick_grid(G, S);
-    DepositGeom G1 = G;
-    if (PAIR) {
-        G1.shift = G.shift + 0.5;
-        if (G.t32 >= 0.f) G1.t32 = G.t32 + 0.5f;
-    }
-    const size_t pages = ((size_t)np * (PAIR ? 2 : 1) + PAGE - 1) / PAGE + B.nbricks;
-    std::vector<VT> pool(pages * PAGE + 1);
-    std::memset(pool.data(), 0xff, pool.size() * sizeof(VT));
-    std::vector<unsigned int> cursor(B.nbricks + 8, 0u), table((size_t)B.nbricks * PAGES_MAX, 0u);
-    unsigned int *pool_next = cursor.data() + B.nbricks + 1;
-    const long long tile = (long long)PART_THREADS * PART_ITEMS;
-    const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)num_sms * 8);
-    simt::launch(pb, PART_THREADS, [&] {
-        brick_partition_kernel<S, PT, SOA, MASS, PAIR, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G, G1, B,
-                                                          cursor.data(), table.data(), pool_next, pool.data(), mesh, mesh1);
-    });
-    if (*pool_next > pages) { std::fprintf(stderr, "simt: page pool overrun (%u > %zu)\n", *pool_next, pages); std::abort(); }
-    simt::launch(B.nbricks, TILE_THREADS, [&] {
-        brick_tile_kernel<S, MASS, VT>(pool.data(), cursor.data(), table.data(), G, B, mesh, PAIR ? 0 : -1);
-    });
-    if (PAIR)
-        simt::launch(B.nbricks, TILE_THREADS, [&] {
-            brick_tile_kernel<S, MASS, VT>(pool.data(), cursor.data(), table.data(), G1, B, mesh1, 1);
-        });
-}
 
 DepositGeom make_geom(int N, double pos_scale, double shift, int resampler, int x0, int n0, int ghost_lo, int ghost_hi) {
     DepositGeom G;
@@ -67,7 +32,6 @@ DepositGeom make_geom(int N, double pos_scale, double shift, int resampler, int 
 template <int S, typename PT, bool SOA, bool MASS, bool PAIR>
 void run(const void *p0, const void *p1, const void *p2, const void *mass, int mass_f64, long long np,
          const DepositGeom &G, float *mesh, float *mesh1, int num_sms) {
-    if (!g_two_pass) return run_paged_host<S, PT, SOA, MASS, PAIR>(p0, p1, p2, mass, mass_f64, np, G, mesh, mesh1, num_sms);
     using VT = typename std::conditional<MASS, P4, P3>::type;
     const BrickGrid B = make_brick_grid(G, S);
     DepositGeom G1 = G;
@@ -96,25 +60,12 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
         brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
                                                         G1, B, cursor.data(), vals.data());
     });
-    // the launcher's choice (run_sorted): unit masses -> particle-parallel fixed-point tile kernel, masses -> per-cell kernel
-    if (!MASS && !g_force_cell_kernel) {
-        if constexpr (!MASS) {
-            simt::launch(B.nbricks, PP_THREADS, [&] {
-                brick_deposit_pp_kernel<S, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, PAIR ? 0 : -1);
-            });
-            if (PAIR)
-                simt::launch(B.nbricks, PP_THREADS, [&] {
-                    brick_deposit_pp_kernel<S, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, mesh1, 1);
-                });
-        }
-        return;
-    }
-    simt::launch(B.nbricks, DEP_THREADS, [&] {
-        brick_deposit_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, PAIR ? 0 : -1);
+    simt::launch(B.nbricks, TILE_THREADS, [&] {
+        brick_tile_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, PAIR ? 0 : -1);
     });
     if (PAIR)
-        simt::launch(B.nbricks, DEP_THREADS, [&] {
-            brick_deposit_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, mesh1, 1);
+        simt::launch(B.nbricks, TILE_THREADS, [&] {
+            brick_tile_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, mesh1, 1);
         });
 }
 
@@ -152,8 +103,6 @@ extern "C" long long simt_deposit_sorted(const void *p0, const void *p1, const v
     return simt::switches;
 }
 
-extern "C" void simt_force_cell_kernel(int on) { g_force_cell_kernel = on; }
-extern "C" void simt_two_pass(int on) { g_two_pass = on; }
 
 // brick_keys for every particle (float32 positions, whole-mesh plan): keys, brick-local coordinates and the split
 // flag of the interlaced pair, for a direct check of the float-register index arithmetic at large mesh sizes.

@@ -206,6 +206,7 @@ inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
 inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
 inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+inline int __float2int_rn(float f) { return (int)std::nearbyintf(f); }      // round to nearest even, like cvt.rni
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 inline int __double2loint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i & 0xffffffffll); }

@@ -102,8 +102,9 @@ class NumpySlabBackend:
         raw[3] = np.bincount(dig, weights=w, minlength=nb1)
         return torch.from_numpy(raw)
 
-    def to_reduce_tensor(self, raw, total):
-        return torch.cat([raw.reshape(-1), total.reshape(1).to(torch.float64)])
+    def to_reduce_tensors(self, raw, total):
+        return (torch.cat([raw[:3].reshape(-1), total.reshape(1).to(torch.float64)]),
+                torch.from_numpy(np.rint(raw[3].numpy()).astype(np.int64)))
 
 
 def _free_port():

@@ -1,8 +1,8 @@
 """What the compiled sm_100a kernels must (not) contain, read from the library's SASS with cuobjdump (no GPU needed).
 
-These are the machine-level facts DESIGN.md section 4 argues from: the tile kernel accumulates in registers (packed
-FFMA2), spreads with shuffles, flushes with fire-and-forget float REDs and never uses a shared-memory float atomic
-(a CAS loop on this architecture) or local memory; the binning kernel evicts with float64 / uint64 REDs.
+These are the machine-level facts DESIGN.md section 4 argues from: the tile kernel accumulates fixed-point integers in
+shared memory with native ATOMS.ADD, flushes with fire-and-forget float REDs and never uses a shared-memory float
+atomic (a CAS loop on this architecture) or local memory; the binning kernel evicts with float64 / uint64 REDs.
 """
 import re
 import shutil
@@ -39,21 +39,24 @@ def count(ops, prefix):
     return sum(op == prefix or op.startswith(prefix + ".") for op in ops)
 
 
-def test_tsc_tile_kernel_is_register_accumulation_plus_reds(sass):
-    ops = one(sass, r"brick_deposit_kernelILi3ELb0ENS_2P3")
-    assert count(ops, "FFMA2") >= 9 * 9              # 9 packed FMAs per particle body, 9 unrolled columns
-    assert count(ops, "SHFL") >= 18 * 9              # z-spread: two shuffles per (a, b), per column
-    assert count(ops, "REDG") == 25                  # one coalesced RED per column of the 5 x 5 window
-    assert not any(op.startswith("ATOMS.CAS") for op in ops), "shared-memory float atomic (CAS loop) in the tile kernel"
-    assert count(ops, "ATOMG") == 0                  # no returning global atomics: one CTA per brick, no work queue
-    assert count(ops, "LDL") + count(ops, "STL") <= 8, "the TSC tile kernel spills"
-    assert count(ops, "BAR") <= 10
+def test_tsc_tile_kernel_is_integer_shared_atomics_plus_reds(sass):
+    ops = one(sass, r"brick_tile_kernelILi3ELb0ENS_2P3")
+    assert count(ops, "ATOMS.ADD") >= 27             # one native integer shared-memory atomic per window cell
+    assert not any(op.startswith("ATOMS.CAS") for op in ops), "shared-memory CAS loop (float atomic) in the tile kernel"
+    assert count(ops, "F2I") <= 8                    # weights become fixed point through the FFMA magic constant, not F2I
+    assert count(ops, "FFMA") >= 27
+    assert count(ops, "REDG") >= 1 and count(ops, "ATOMG") == 0      # flush: fire-and-forget float REDs
+    assert count(ops, "LDL") + count(ops, "STL") == 0, "the TSC tile kernel spills"
+    assert count(ops, "BAR") <= 6
 
 
-def test_cic_tile_kernel_flushes_a_4x4_window(sass):
-    ops = one(sass, r"brick_deposit_kernelILi2ELb0ENS_2P3")
-    assert count(ops, "REDG") == 16
-    assert not any(op.startswith("ATOMS.CAS") for op in ops)
+def test_cic_and_mass_tile_kernels(sass):
+    ops = one(sass, r"brick_tile_kernelILi2ELb0ENS_2P3")
+    assert count(ops, "ATOMS.ADD") >= 8 and not any(op.startswith("ATOMS.CAS") for op in ops)
+    ops = one(sass, r"brick_tile_kernelILi3ELb1ENS_2P4")
+    assert count(ops, "ATOMS.ADD") >= 27 and not any(op.startswith("ATOMS.CAS") for op in ops)
+    assert count(ops, "F2I") >= 27                   # with masses: FMUL + F2I at the chunk's own scale
+    assert count(ops, "LDL") + count(ops, "STL") == 0
 
 
 def test_partition_counts_with_reds_and_scatters_with_returning_atomics(sass):

@@ -174,10 +174,9 @@ def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):
     The scheduler (random warp subsets and single-warp bursts) must turn that into a wrong mesh."""
     import build_simt
     src = build_simt.device_part(os.path.join(build_simt.CSRC, "deposit_sorted.cu"))
-    paged = build_simt.paged_device_part()
     barrier = "__syncthreads();   // every particle of the chunk is in the tile"
-    assert paged.count(barrier) == 1
-    lib = load(build_simt.compile_kernels(src, str(tmp_path), paged_text=paged.replace(barrier, "(void)0;")))
+    assert src.count(barrier) == 1
+    lib = load(build_simt.compile_kernels(src.replace(barrier, "(void)0;"), str(tmp_path)))
     rng = np.random.default_rng(3)
     N, L = 32, 32.0
     pos = np.concatenate([rng.random((9000, 3)) * L, rng.random((5000, 3)) * [10.0, 5.0, 20.0] + 1.0]).astype(np.float32)
