@@ -9,7 +9,13 @@
 
 namespace apk {
 
-constexpr int BX = 12, BY = 6;                  // brick edge in cells along x, y
+#ifndef APK_BX
+#define APK_BX 12
+#endif
+#ifndef APK_BY
+#define APK_BY 6
+#endif
+constexpr int BX = APK_BX, BY = APK_BY;         // brick edge in cells along x, y
 constexpr int BZ = 32;                          // z-lanes of a column = tile cells along z (one warp)
 // home cells along z: 32 - (S-1), so that a column's 32 lanes are exactly its 32 tile cells
 // (30 home cells + 2 halo lanes for TSC, 31 + 1 for CIC) and the spread needs no halo special case

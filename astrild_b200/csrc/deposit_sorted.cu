@@ -228,16 +228,25 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 //   fixed-point value).  Integer adds commute: a brick's contribution to the mesh does not depend on the order in
 //   which the partition filed its particles.
 //   The tile goes to the mesh as one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
-constexpr int TILE_FLUSH = 4095;                      // particles between two flushes of the tile
+#ifndef APK_TILE_FLUSH
+#define APK_TILE_FLUSH 4095
+#endif
+constexpr int TILE_FLUSH = APK_TILE_FLUSH;            // particles between two flushes of the tile
 constexpr int TILE_THREADS = 256;
 #ifndef APK_TILE_CTAS
 #define APK_TILE_CTAS 6
 #endif
 
+#ifndef APK_TILE_ZSTRIDE
+#define APK_TILE_ZSTRIDE 33
+#endif
+// The tile is [TX][TY] columns of TZ = 32 cells along z, ZS words apart.  ZS = 33 skews the columns over the banks
+// (bank = z + y + 8 x mod 32): two particles of one warp then collide when their CELLS coincide modulo that skew, not
+// whenever their z alone does -- snapshot-ordered particles are neighbours along z, displaced by a cell or so.
 template <int S> struct Tile {
     static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
-    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ;
-    static constexpr int CELLS = TX * TY * TZ;
+    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ, ZS = APK_TILE_ZSTRIDE;
+    static constexpr int CELLS = TX * TY * ZS;
 };
 
 // fractional bits for a chunk of n unit-mass particles: n * wmax * 2^s < 2^32, s <= SMAX (the magic-constant trick
@@ -357,7 +366,7 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
 #pragma unroll
                     for (int a = 0; a < S; ++a) wx[a] *= m;
                 }
-                unsigned int *cell = tile + (hx * T::TY + hy) * T::TZ + hz;     // window origin (home - OFF) in tile coordinates
+                unsigned int *cell = tile + (hx * T::TY + hy) * T::ZS + hz;     // window origin (home - OFF) in tile coordinates
 #pragma unroll
                 for (int a = 0; a < S; ++a)
 #pragma unroll
@@ -367,7 +376,7 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
                         for (int c = 0; c < S; ++c) {
                             const unsigned int fx = MASS ? (unsigned int)__float2int_rn(wxy * wz[c])
                                                          : (unsigned int)__float_as_int(fmaf(wxy, wz[c], magic)) - magic_bits;
-                            atomicAdd(cell + (a * T::TY + b) * T::TZ + c, fx);
+                            atomicAdd(cell + (a * T::TY + b) * T::ZS + c, fx);
                         }
                     }
             }
@@ -378,8 +387,8 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
             const int x0 = bx * BX - T::OFF, y0 = by * BY - T::OFF;
             for (int col = warp; col < T::TX * T::TY; col += TILE_THREADS / 32) {
                 const int u = col / T::TY, w = col - u * T::TY;
-                const unsigned int fx = tile[col * T::TZ + lane];
-                if (c1 < pend) tile[col * T::TZ + lane] = 0u;
+                const unsigned int fx = tile[col * T::ZS + lane];
+                if (c1 < pend) tile[col * T::ZS + lane] = 0u;
                 int px = x0 + u;
                 bool ok = true;
                 if (G.slab) ok = px >= 0 && px < G.nplanes;
