@@ -176,6 +176,25 @@ int apk_bin_power(apk_binning *binning, const void *c1, const void *c1s, const v
                   const void *c2s, double *ksum, double *psum_re, double *psum_im,
                   int64_t *nmodes, void *stream);
 
+/* ---- ingest ------------------------------------------------------------------- */
+/* PowerSpectrum3D._read_data's gridder (src/astrild/power_spectra/power_spectrum_3d.py:142-148):
+ *   value_map = zeros((N, N, N)); value_map[((N*x).astype(int), (N*y).astype(int), (N*z).astype(int))] = values
+ * One value per cell (assignment, not accumulation); the product is formed in the dtype of the coordinate columns and
+ * truncated toward zero; a negative index wraps once like NumPy's; a cell hit by several samples keeps the value of the
+ * LAST one (highest index).  x, y, z, values: DEVICE arrays of n entries; value_map: DEVICE float64 [N][N][N], cleared by
+ * the call; winner_scratch: DEVICE uint32 [N^3]; bad_count_dev: DEVICE uint64 that receives the number of samples whose
+ * index lies outside [-N, N) (NumPy raises IndexError for those: the host side does the same).                      */
+int apk_assign_grid(apk_plan *plan, const void *x, const void *y, const void *z, int pos_dtype, const void *values,
+                    int val_dtype, int64_t n, double *value_map, uint32_t *winner_scratch, uint64_t *bad_count_dev,
+                    void *stream);
+/* Ecosmog.compress_snapshot's record reader (src/astrild/particles/ecosmog.py:184-230) on the device: raw_dev is the
+ * image of an output_poisson file (Fortran unformatted records); pieces_dev is int64 [npieces][3] = (byte offset of a
+ * block of float64 values in the image -- 4-byte aligned, record markers are 4 bytes --, first destination element,
+ * number of values); every block is copied into out[dst .. dst + count).  The host walks the record headers
+ * (astrild_b200/ingest.py) and this kernel moves the data: one CTA per piece.                                     */
+int apk_gather_records(const void *raw_dev, const int64_t *pieces_dev, int64_t npieces, double *out, int device,
+                       void *stream);
+
 /* ---- binning tables (host side of FFTPower: who decides which float lands on which side of an edge) ---- */
 /* The per-axis tables and edges apk_binning_create takes, computed INSIDE the library with the reference stack's
  * expression order (pmesh ParticleMesh k tables: w = n * (2 pi / N), k = w * N / L; nbodykit FFTPower:
