@@ -8,26 +8,24 @@
 // traffic is real but not credited.
 //
 // Pipeline (all on one stream, no host sync):
-//   1. brick_count_kernel   every particle -> key of the brick (12 x 6 x 30 home cells for TSC, 12 x 6 x 31
-//                           for CIC) that holds its HOME cell; per-brick counts with one RED per warp-run of
-//                           equal keys (snapshot order is spatially coherent).  float32 positions use an
-//                           error-free float32 product (no FP64 issue slots), float64 positions the oracle's
-//                           float64 expression; both put every particle in the oracle's cell.
+//   1. brick_count_kernel   every particle -> key of the brick (12 x 6 x 29..31 home cells) that holds its mesh-0 HOME
+//                           cell; per-brick counts with one RED per warp-run of equal keys (snapshot order is spatially
+//                           coherent).  float32 positions: ~40 FP32 instructions per particle, no float64, no
+//                           conversions, no integer division (brick_keys_f32); float64 positions: the oracle's expression.
 //   2. brick_scan_kernel    exclusive scan of the counts -> brick_start[], cursors, list of non-empty bricks.
 //   3. brick_scatter_kernel keys are recomputed (never stored); each run of equal keys claims its slots with ONE
 //                           atomicAdd on the brick's cursor and writes its payload = brick-local coordinates as
 //                           3 floats (+ mass), contiguously.  One read and one write of the particles replace a
 //                           multi-pass radix sort; order inside a brick is arbitrary (the deposit does not care).
-//      PAIR mode (apk_deposit_interlaced): one partition serves both interlaced meshes -- particles whose
-//      two home cells fall in different bricks are filed twice, sign bits of the payload say which
-//      mesh a copy is for.
+//      Interlaced pair (apk_deposit_interlaced): the SAME partition and the same 12-byte payload serve both meshes --
+//      the twin's home cell is the same cell or the next one per axis, so its tile is one cell longer per axis
+//      (bricks hold one z-cell less) and its coordinates are the payload's + 0.5.  No second copies, no flags.
 //   4. brick_tile_kernel    one CTA per non-empty brick, one THREAD per particle, the brick's window of the mesh as
 //                           fixed-point integers in shared memory, native ATOMS.ADD (see the kernel's comment).
-//      A one-pass partition into paged buckets (pages handed out as the cursors cross page boundaries, no count
-//      pass) was built and measured in round 2: 21.7 ms against 7.5 + 9.4 ms for count + scatter at 1024^3 -- the
-//      page-table look-up sits on the store's critical path -- and its wait for a page that another thread has yet to
-//      publish can dead-lock when a thread's two in-flight claims complete out of order (it did, on randomly ordered
-//      input).  It was removed; profiles/r02_measurements.md has the numbers.
+//      Tried and removed in round 2 (profiles/r02_measurements.md): a one-pass partition into paged buckets (21.7 ms
+//      against 7.5 + 9.4 ms for count + scatter at 1024^3, and it can dead-lock on randomly ordered input); filing the
+//      twin's boundary particles twice with sign flags (14 % more payload, ~110 more instructions per particle in
+//      each partition pass).
 #include "brick_common.cuh"
 #include <algorithm>
 #include <cstdint>
@@ -36,13 +34,10 @@
 namespace apk {
 
 
-// PAIR: one partition serves the interlaced twins (G: shift 0, G1: shift 0.5).  Every particle is filed
-// under the brick of its mesh-0 home cell; the ~11 % whose mesh-1 home cell lies in a different brick get
-// a second, mesh-1-only copy there (the first copy is then flagged mesh-0-only).
-template <int S, typename PT, bool SOA, bool PAIR>
+template <int S, typename PT, bool SOA>
 __global__ void __launch_bounds__(PART_THREADS)
 brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2, long long np,
-                   DepositGeom G, DepositGeom G1, BrickGrid B, unsigned int *__restrict__ counts) {
+                   DepositGeom G, BrickGrid B, unsigned int *__restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     const long long step = (long long)gridDim.x * tile;
@@ -55,18 +50,13 @@ brick_count_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const P
         if (base + step < np) load4<PT, SOA>(p0, p1, p2, first + step, PART_THREADS, np, nxt);   // next tile in flight
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float l[3], l1[3];
-            unsigned int key, key1;
-            bool split;
-            brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1, split);
+            float l[3];
+            unsigned int key;
+            brick_keys<S, PT>(cur.v + 3 * k, G, B, key, l);
             if (first + (long long)k * PART_THREADS >= np) key = 0xffffffffu;
             int head, offset, length;
             warp_runs(key, lane, head, offset, length);
             if (key != 0xffffffffu && offset == 0) atomicAdd(counts + key, (unsigned int)length);
-            if constexpr (PAIR) {
-                const bool extra = key != 0xffffffffu && split;
-                if (__any_sync(0xffffffffu, extra) && extra) atomicAdd(counts + key1, 1u);
-            }
         }
     }
 }
@@ -142,15 +132,13 @@ brick_scan_kernel(const unsigned int *__restrict__ counts, int n, const unsigned
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 1023) { start[n] = base + total; *nfilled = fbase + ftotal; }
 }
 
-// PAIR payload: u + 1 per axis, u = unshifted coordinate relative to the brick origin (>= -1); the sign
-// of x says "not for mesh 0", the sign of y "not for mesh 1".
 #ifndef APK_SCATTER_MIN_CTAS
 #define APK_SCATTER_MIN_CTAS 3
 #endif
-template <int S, typename PT, bool SOA, bool MASS, bool PAIR, typename VT>
+template <int S, typename PT, bool SOA, bool MASS, typename VT>
 __global__ void __launch_bounds__(PART_THREADS, APK_SCATTER_MIN_CTAS)
 brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
-                     const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G, DepositGeom G1,
+                     const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G,
                      BrickGrid B, unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
@@ -164,22 +152,21 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
         if (base + step < np) load4<PT, SOA>(p0, p1, p2, first + step, PART_THREADS, np, nxt);   // next tile in flight
         // Software pipeline of depth one: item k claims its slots (returning atomics, ~600 cycles) and item k-1,
         // whose slots have arrived meanwhile, is stored.
-        VT pv = {}, pw = {};
-        unsigned int pslot = 0, pslot1 = 0;
+        VT pv = {};
+        unsigned int pslot = 0;
         int phead = 0, poffset = 0;
-        bool plive = false, pextra = false;
+        bool plive = false;
 #pragma unroll
         for (int k = 0; k <= 4; ++k) {
-            VT v = {}, w = {};
-            unsigned int slot = 0, slot1 = 0;
+            VT v = {};
+            unsigned int slot = 0;
             int head = 0, offset = 0, length = 0;
-            bool live = false, extra = false;
+            bool live = false;
             if (k < 4) {
                 const long long p = first + (long long)k * PART_THREADS;
-                float l[3], l1[3];
-                unsigned int key, key1;
-                bool split;
-                brick_keys<S, PT, PAIR>(cur.v + 3 * k, G, G1, B, key, l, key1, l1, split);
+                float l[3];
+                unsigned int key;
+                brick_keys<S, PT>(cur.v + 3 * k, G, B, key, l);
                 if (p >= np) key = 0xffffffffu;
                 live = key != 0xffffffffu;
                 v.x = l[0]; v.y = l[1]; v.z = l[2];
@@ -187,29 +174,14 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
                     const long long pc = min(p, np - 1);
                     v.m = mass_f64 ? (float)((const double *)mass)[pc] : ((const float *)mass)[pc];
                 }
-                if constexpr (PAIR) {
-                    v.x = fmaxf(l[0] + 1.f, 0.f); v.y = fmaxf(l[1] + 1.f, 0.f); v.z = fmaxf(l[2] + 1.f, 0.f);
-                    if (split) v.y = -v.y;                           // first copy is mesh-0-only
-                }
                 warp_runs(key, lane, head, offset, length);
                 if (live && offset == 0) slot = atomicAdd(cursor + key, (unsigned int)length);
-                if constexpr (PAIR) {
-                    extra = live && split;
-                    if (extra) {                                     // second copy: mesh-1-only, in mesh 1's brick
-                        w = v;
-                        w.x = -fmaxf(l1[0] + 0.5f, 0.f); w.y = fmaxf(l1[1] + 0.5f, 0.f); w.z = fmaxf(l1[2] + 0.5f, 0.f);
-                        slot1 = atomicAdd(cursor + key1, 1u);
-                    }
-                }
             }
             if (k > 0) {
                 const unsigned int ps = __shfl_sync(0xffffffffu, pslot, phead) + poffset;
                 if (plive) vals[ps] = pv;
-                if constexpr (PAIR) {
-                    if (pextra) vals[pslot1] = pw;
-                }
             }
-            pv = v; pw = w; pslot = slot; pslot1 = slot1; phead = head; poffset = offset; plive = live; pextra = extra;
+            pv = v; pslot = slot; phead = head; poffset = offset; plive = live;
         }
     }
 }
@@ -217,16 +189,23 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 // ---------------------------------------------------------------------------------------------------------------
 // Tile kernel: one CTA per brick, one THREAD per particle.  The brick's window of the mesh lives in shared memory as
 // 32-bit FIXED-POINT integers and every one of the S^3 weights goes there with a native integer ATOMS.ADD (measured on
-// B200, tools/ubench/atoms.cu: 0.7 cycles per warp-instruction and SM without bank conflicts, 1.9 with random cells;
-// the float atomicAdd is a CAS loop at 3.5 - 9.6).  No in-brick sort, no per-cell loop: all 32 lanes work on every
-// instruction, whatever the cell occupancy.
+// B200, tools/ubench/atoms.cu: 0.7 cycles per warp-instruction and SM when the 32 lanes hit 32 banks, 0.7 k when k lanes
+// share a bank -- the SAME address counts like any other bank conflict -- and ~1.9 for random cells; the float atomicAdd
+// is a CAS loop at 3.5 - 9.6).  No in-brick sort, no per-cell loop: all 32 lanes work on every instruction, whatever the
+// cell occupancy.  ncu (profiles/): the shared-memory pipe is what bounds this kernel (> 85 % busy with ATOMS
+// wavefronts, 3.3 per instruction); particle order inside the brick does not change that (measured: input order,
+// shuffled and cell-sorted sets within 10 %, the cell-sorted one slowest).
 //   Quantum: 2^-s of the largest |mass| in the chunk (1 for unit masses), s chosen PER CHUNK of <= TILE_FLUSH particles
 //   as large as 32 bits allow if every particle of the chunk put its largest possible weight (1 for CIC, 0.75^3 for
 //   TSC) into one cell: s = 22 for the ~2200 particles of a brick at one particle per cell (TSC), 20 - 21 for a full
-//   chunk, up to 23 for sparse bricks.  A weight is rounded to the quantum by ONE FFMA against a magic constant
-//   (1.5 * 2^(23 - s): the sum lands in a binade whose ulp is the quantum, so the low mantissa bits ARE the
-//   fixed-point value).  Integer adds commute: a brick's contribution to the mesh does not depend on the order in
-//   which the partition filed its particles.
+//   chunk, up to 24 for sparse bricks.
+//   Unit masses: the float -> fixed conversion costs nothing.  The three axis weights carry the factors 2^-40, 2^-40 and
+//   2^(s - 69), so the product of the three is w * 2^(s - 149): a SUBNORMAL float whose bit pattern IS the integer
+//   rint(w * 2^s) (the one rounding of the last FMUL is to the subnormal grid, round-to-nearest-even; no intermediate is
+//   subnormal).  One FMUL + one ATOMS.ADD per cell.  (Needs denormal support: the library is built without -ftz.)
+//   Per-particle masses: FMUL + F2I (signed; the scale comes from the chunk's sum of |mass|).
+//   Integer adds commute: a brick's contribution to the mesh does not depend on the order in which the partition
+//   filed its particles.
 //   The tile goes to the mesh as one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
 #ifndef APK_TILE_FLUSH
 #define APK_TILE_FLUSH 4095
@@ -241,27 +220,26 @@ constexpr int TILE_THREADS = 256;
 #define APK_TILE_ZSTRIDE 32
 #endif
 // The tile is [TX][TY] columns of TZ = 32 cells along z, ZS words apart.  ZS = 32: the bank of a cell is its z alone.
-// Snapshot-ordered particles are neighbours along z, so the 32 particles of a warp mostly sit in 30 DIFFERENT z-cells
-// (plus their displacements): measured at 1024^3, ZS = 33 (columns skewed over the banks, collisions as for random
-// cells) is 15 % slower (27.2 against 23.7 ms for both meshes), and so are larger bricks (16 x 16, 24 x 12: 25.8 - 27 ms).
-template <int S> struct Tile {
+// Measured at 1024^3: ZS = 33 (columns skewed over the banks) is 15 % slower on snapshot-ordered input (27.2 against
+// 23.7 ms for both meshes), and so are larger bricks (16 x 16, 24 x 12: 25.8 - 27 ms).
+template <int S, bool PAIR> struct Tile {
     static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
-    static constexpr int TX = BX + S - 1, TY = BY + S - 1, TZ = BZ, ZS = APK_TILE_ZSTRIDE;
+    static constexpr int TX = BX + S - 1 + (PAIR ? 1 : 0), TY = BY + S - 1 + (PAIR ? 1 : 0), TZ = BZ, ZS = APK_TILE_ZSTRIDE;
     static constexpr int CELLS = TX * TY * ZS;
 };
 
-// fractional bits for a chunk of n unit-mass particles: n * wmax * 2^s < 2^32, s <= SMAX (the magic-constant trick
-// needs wmax <= 2^(22 - s))
+// fractional bits for a chunk of n unit-mass particles: n * wmax * 2^s < 2^32, s <= SMAX (a single weight must stay
+// below 2^24 quanta, where float bit patterns stop being linear in the value)
 template <int S>
 __device__ __forceinline__ int tile_frac_bits(int n) {
     constexpr float WMAX = (S == 3) ? 0.43f : 1.001f;          // 0.75^3 = 0.4219 / 1, padded for the rounding
-    constexpr int SMAX = (S == 3) ? 23 : 22;
+    constexpr int SMAX = (S == 3) ? 24 : 23;
     const float room = (4294967296.f / WMAX) / (float)n;
     const int s = ((__float_as_int(room) >> 23) & 0xff) - 127;  // floor(log2(room))
     return min(s, SMAX);
 }
 
-// nearest brick-local home cell of coordinate l on one axis (clamped to the brick) as float and int, and the offset
+// nearest brick-local home cell of coordinate l on one axis (clamped to the brick) as int, and the offset
 // d = l - home: [-0.5, 0.5] for TSC, [0, 1] for CIC (ties land on either side; the windows are continuous there)
 template <int S>
 __device__ __forceinline__ void tile_home(float l, float last, float &d, int &h) {
@@ -270,17 +248,27 @@ __device__ __forceinline__ void tile_home(float l, float last, float &d, int &h)
     t = fminf(fmaxf(t, M), M + last);
     h = __float_as_int(t) & 0x3fffff;
     d = l - (t - M);
+    // CIC: a coordinate within rounding of the brick's faces may leave [0, 1] by ~1e-5; the weights d and 1 - d must not
+    // turn negative (the unit-mass path reads the bit pattern of the product as an unsigned integer).  TSC's are
+    // squares and 0.75 - d^2: positive for any |d| < 0.86.
+    if (S == 2) d = fminf(fmaxf(d, 0.f), 1.f);
 }
 
-template <int S, bool MASS, typename VT>
+// sel: 0 = mesh 0 (or the only mesh), 1 = the interlaced twin (coordinates + 0.5, home cells one further)
+template <int S, bool MASS, bool PAIR, typename VT>
 __global__ void __launch_bounds__(TILE_THREADS, APK_TILE_CTAS)
 brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
                   const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
                   DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
-    using T = Tile<S>;
-    __shared__ unsigned int tile[T::CELLS];
+    using T = Tile<S, PAIR>;
+    constexpr int ZC = BrickZ<S, PAIR>::CELLS;
+    __shared__ __align__(16) unsigned int tile[T::CELLS];
+    __shared__ long long xoff[T::TX];                 // mesh offset of the tile's x-planes (-1: outside the slab)
+    __shared__ int yoff[T::TY];                       // ... and of its y-rows
     __shared__ float red_s[2 * (TILE_THREADS / 32)];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float twin = sel > 0 ? 0.5f : 0.f;
+    const float lastx = (float)(BX - 1 + (sel > 0)), lasty = (float)(BY - 1 + (sel > 0)), lastz = (float)(ZC - 1 + (sel > 0));
 
     // One CTA per non-empty brick, in list order (x-major: neighbouring windows meet in L2).  CTAs retire all the
     // time, so kernels of a higher-priority stream (the slab path's FFT / transpose of the first mesh) get SMs while
@@ -294,15 +282,23 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
         const int bx = brick / (B.nbz * B.nby);
 
         __syncthreads();                              // (persistent grids) the previous brick's flush is complete
-        for (int i = tid; i < T::CELLS; i += TILE_THREADS) tile[i] = 0u;
+        for (int i = tid; i < T::CELLS / 4; i += TILE_THREADS) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < T::TX) {
+            int px = bx * BX - T::OFF + tid;
+            bool ok = true;
+            if (G.slab) ok = px >= 0 && px < G.nplanes;
+            else px = wrap_index32(px, G.N);
+            xoff[tid] = ok ? (long long)px * G.N * G.ldz : -1LL;
+        } else if (tid < T::TX + T::TY) {
+            yoff[tid - T::TX] = wrap_index32(by * BY - T::OFF + tid - T::TX, G.N) * G.ldz;
+        }
         __syncthreads();
 
         for (unsigned int c0 = pbeg; c0 < pend; c0 += TILE_FLUSH) {
             const unsigned int c1 = min(c0 + (unsigned int)TILE_FLUSH, pend);
             // ---- masses: unit = the power of two at or above the chunk's largest |mass| (scaling by it is exact), and
             //      the fixed-point scale from the chunk's sum of |mass|: no cell can overflow 31 bits + sign even if
-            //      every particle put its largest weight into it.  The conversion is FMUL + F2I here (the magic-constant
-            //      trick would cap the scale at 2^22 / unit, too coarse when the masses span decades).
+            //      every particle put its largest weight into it.
             float unit = 1.f, inv_unit = 1.f, mscale = 1.f;
             int frac_bits = 0;
             if constexpr (MASS) {
@@ -335,37 +331,37 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
             } else {
                 frac_bits = tile_frac_bits<S>((int)(c1 - c0));
             }
-            const unsigned int magic_bits = ((unsigned int)(127 + 23 - (MASS ? 0 : frac_bits)) << 23) | 0x400000u;   // 1.5 * 2^(23 - s)
-            const float magic = __int_as_float((int)magic_bits);
             const float quantum = __int_as_float((127 - frac_bits) << 23) * unit;                         // 2^-s mass units
+            // unit masses: axis factors 2^-40 (x), 2^-40 (y), 2^(s - 69) (z); masses: 1, 1, m * 2^s
+            const float KXY = MASS ? 1.f : __int_as_float((127 - 40) << 23);
+            const float KZ = MASS ? 1.f : __int_as_float((127 + frac_bits - 69) << 23);
 
             // ---- one thread per particle; the next particle's loads are in flight while this one is deposited ----
             unsigned int p = c0 + tid;
             VT nxt = {};
             if (p < c1) nxt = vals[p];
             for (; p < c1; p += TILE_THREADS) {
-                VT v = nxt;
+                const VT v = nxt;
                 const unsigned int q = p + TILE_THREADS;
                 if (q < c1) nxt = vals[q];
-                if (!unpack_pair(v, sel)) continue;
                 float dx, dy, dz;
                 int hx, hy, hz;
-                tile_home<S>(v.x, (float)(BX - 1), dx, hx);
-                tile_home<S>(v.y, (float)(BY - 1), dy, hy);
-                tile_home<S>(v.z, (float)(BrickZ<S>::CELLS - 1), dz, hz);
+                tile_home<S>(v.x + twin, lastx, dx, hx);
+                tile_home<S>(v.y + twin, lasty, dy, hy);
+                tile_home<S>(v.z + twin, lastz, dz, hz);
+                float kz = KZ;
+                if constexpr (MASS) kz = (v.m * inv_unit) * mscale;              // |m / unit| <= 1, exact; times 2^s
                 float wx[S], wy[S], wz[S];
                 if (S == 2) {
-                    wx[0] = 1.f - dx; wx[S - 1] = dx; wy[0] = 1.f - dy; wy[S - 1] = dy; wz[0] = 1.f - dz; wz[S - 1] = dz;
+                    wx[S - 1] = dx * KXY; wx[0] = KXY - wx[S - 1];
+                    wy[S - 1] = dy * KXY; wy[0] = KXY - wy[S - 1];
+                    wz[S - 1] = dz * kz;  wz[0] = kz - wz[S - 1];
                 } else {
                     const float ax = 0.5f - dx, cx = 0.5f + dx, ay = 0.5f - dy, cy = 0.5f + dy, az = 0.5f - dz, cz = 0.5f + dz;
-                    wx[0] = 0.5f * ax * ax; wx[S / 2] = fmaf(-dx, dx, 0.75f); wx[S - 1] = 0.5f * cx * cx;
-                    wy[0] = 0.5f * ay * ay; wy[S / 2] = fmaf(-dy, dy, 0.75f); wy[S - 1] = 0.5f * cy * cy;
-                    wz[0] = 0.5f * az * az; wz[S / 2] = fmaf(-dz, dz, 0.75f); wz[S - 1] = 0.5f * cz * cz;
-                }
-                if constexpr (MASS) {
-                    const float m = (v.m * inv_unit) * mscale;                   // |m / unit| <= 1, exact; times 2^s
-#pragma unroll
-                    for (int a = 0; a < S; ++a) wx[a] *= m;
+                    const float hxy = 0.5f * KXY, hz2 = 0.5f * kz;
+                    wx[0] = (ax * hxy) * ax; wx[S / 2] = fmaf(-dx, dx, 0.75f) * KXY; wx[S - 1] = (cx * hxy) * cx;
+                    wy[0] = (ay * hxy) * ay; wy[S / 2] = fmaf(-dy, dy, 0.75f) * KXY; wy[S - 1] = (cy * hxy) * cy;
+                    wz[0] = (az * hz2) * az; wz[S / 2] = fmaf(-dz, dz, 0.75f) * kz;  wz[S - 1] = (cz * hz2) * cz;
                 }
                 unsigned int *cell = tile + (hx * T::TY + hy) * T::ZS + hz;     // window origin (home - OFF) in tile coordinates
 #pragma unroll
@@ -376,7 +372,7 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
 #pragma unroll
                         for (int c = 0; c < S; ++c) {
                             const unsigned int fx = MASS ? (unsigned int)__float2int_rn(wxy * wz[c])
-                                                         : (unsigned int)__float_as_int(fmaf(wxy, wz[c], magic)) - magic_bits;
+                                                         : __float_as_uint(__fmul_rn(wxy, wz[c]));
                             atomicAdd(cell + (a * T::TY + b) * T::ZS + c, fx);
                         }
                     }
@@ -384,19 +380,16 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
             __syncthreads();   // every particle of the chunk is in the tile
 
             // ---- tile -> mesh: one coalesced 128-byte RED per (x,y) column, zeros skipped; the tile is cleared on the way ----
-            const int gz = wrap_index32(bz * BrickZ<S>::CELLS - T::OFF + lane, G.N);
-            const int x0 = bx * BX - T::OFF, y0 = by * BY - T::OFF;
+            float *mz = mesh + wrap_index32(bz * ZC - T::OFF + lane, G.N);
+            const bool more = c1 < pend;
             for (int col = warp; col < T::TX * T::TY; col += TILE_THREADS / 32) {
                 const int u = col / T::TY, w = col - u * T::TY;
                 const unsigned int fx = tile[col * T::ZS + lane];
-                if (c1 < pend) tile[col * T::ZS + lane] = 0u;
-                int px = x0 + u;
-                bool ok = true;
-                if (G.slab) ok = px >= 0 && px < G.nplanes;
-                else px = wrap_index32(px, G.N);
-                if (ok && fx != 0u) {
+                if (more) tile[col * T::ZS + lane] = 0u;
+                const long long xo = xoff[u];
+                if (fx != 0u && xo >= 0) {
                     const float val = MASS ? (float)(int)fx * quantum : (float)fx * quantum;
-                    atomicAdd(mesh + ((long long)px * G.N + wrap_index32(y0 + w, G.N)) * G.ldz + gz, val);
+                    atomicAdd(mz + xo + yoff[w], val);
                 }
             }
             __syncthreads();
@@ -405,15 +398,15 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
 }
 
 static size_t max_bricks(const apk_plan *P) {
-    return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + 29) / 30);
+    return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + 28) / 29);
 }
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
-// pair != 0: room for the interlaced twins' shared partition (every particle may need two copies)
-size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int pair) {
+// pair: the interlaced twins share one partition and one payload -- no extra room needed
+size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int /*pair*/) {
     if (np <= 0) return 0;
     const size_t vs = with_mass ? sizeof(P4) : sizeof(P3);
-    return align256(vs * (size_t)np * (pair ? 2 : 1)) + 4 * align256(4 * (max_bricks(P) + 2)) +
+    return align256(vs * (size_t)np) + 4 * align256(4 * (max_bricks(P) + 2)) +
            2 * align256(4 * (max_bricks(P) / SCAN_SEG + 2)) + 256;
 }
 
@@ -422,21 +415,16 @@ template <int S, typename PT, bool SOA, bool MASS, bool PAIR>
 static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p2, const void *mass,
                       int mass_dtype, long long np, const DepositGeom &G, float *mesh, float *mesh1, cudaStream_t st) {
     using VT = typename std::conditional<MASS, P4, P3>::type;
-    const BrickGrid B = make_brick_grid(G, S);
-    DepositGeom G1 = G;
-    if (PAIR) {
-        G1.shift = G.shift + 0.5;
-        if (G.t32 >= 0.f) G1.t32 = G.t32 + 0.5f;
-    }
+    const BrickGrid B = make_brick_grid(G, S, PAIR);
     const size_t need = deposit_sorted_workspace_bytes(P, np, MASS, PAIR);
-    APK_REQUIRE(!PAIR || 2 * np < 0xffffffffLL, "apk_deposit_interlaced: more than 2^31 - 1 particles on one device");
     // the cuFFT work areas live in the last fft_work_bytes of the same workspace and may be in use on another stream
     APK_REQUIRE(P->workspace && P->workspace_bytes >= need + P->fft_work_bytes + 256,
                 "apk_deposit: sorted path needs %zu workspace bytes (+ %zu of cuFFT work area), %zu set "
                 "(apk_plan_workspace_bytes / apk_plan_set_workspace)", need, P->fft_work_bytes + 256, P->workspace_bytes);
     APK_REQUIRE(np < 0xffffffffLL, "apk_deposit: more than 2^32-1 particles on one device");
+    APK_REQUIRE((size_t)B.nbricks <= max_bricks(P), "apk_deposit: brick tables too small (internal)");
     unsigned char *w = (unsigned char *)P->workspace;
-    VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np * (PAIR ? 2 : 1));
+    VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np);
     const size_t tab = align256(4 * (max_bricks(P) + 2));
     unsigned int *counts = (unsigned int *)w; w += tab;
     unsigned int *brick_start = (unsigned int *)w; w += tab;
@@ -450,7 +438,7 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)P->num_sms * 8);
     P->mark(0, st);
     APK_CUDA(cudaMemsetAsync(counts, 0, 4 * (size_t)(B.nbricks + 1), st));
-    brick_count_kernel<S, PT, SOA, PAIR><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, G1, B, counts);
+    brick_count_kernel<S, PT, SOA><<<pb, PART_THREADS, 0, st>>>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts);
     APK_CUDA(cudaGetLastError());
     P->mark(1, st);
     const int nseg = (B.nbricks + SCAN_SEG - 1) / SCAN_SEG;
@@ -459,19 +447,19 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     brick_scan_kernel<<<nseg, 1024, 0, st>>>(counts, B.nbricks, seg_total, seg_filled, brick_start, cursor, filled, counter + 1);
     APK_CUDA(cudaGetLastError());
     P->mark(2, st);
-    brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT><<<pb, PART_THREADS, 0, st>>>(
-        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, G1, B, cursor, vals);
+    brick_scatter_kernel<S, PT, SOA, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
+        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
 
     // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
     const int ctas = B.nbricks;
-    auto kern = brick_tile_kernel<S, MASS, VT>;
+    auto kern = brick_tile_kernel<S, MASS, PAIR, VT>;
     P->mark(3, st);
-    kern<<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, PAIR ? 0 : -1);
+    kern<<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, 0);
     APK_CUDA(cudaGetLastError());
     if (PAIR) {
         if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
-        kern<<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G1, B, mesh1, 1);
+        kern<<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh1, 1);
         APK_CUDA(cudaGetLastError());
     }
     P->mark(4, st);

@@ -316,6 +316,16 @@ def run_ours(args, wl_key: str) -> None:
         runner.profile = True
     else:
         pos, halos = make_particles(wl, dev)
+        if args.order != "input":
+            if args.order == "cell":
+                key = (pos[0] * N).long().clamp_(0, N - 1)
+                key = (key * N + (pos[1] * N).long().clamp_(0, N - 1)) * N + (pos[2] * N).long().clamp_(0, N - 1)
+                perm = torch.argsort(key)
+                del key
+            else:
+                perm = torch.randperm(pos[0].numel(), device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+            pos = tuple(c[perm].contiguous() for c in pos)
+            del perm
         torch.cuda.empty_cache()
         eng = ab.get_engine(N, L, dev)
         comp = (wl["resampler"], wl["interlaced"]) if wl["compensated"] else None
@@ -560,6 +570,8 @@ def run_ours(args, wl_key: str) -> None:
               "l2": "inputs >> L2 (126 MB): no flush needed"}
     if cross:
         config["halos"] = Nh
+    if getattr(args, "order", "input") != "input":
+        config["particle_order"] = args.order + " (diagnostic reordering of the set)"
     if world > 1 and slab_info:
         config["transpose"] = slab_info.get("transpose")
         config["critical_path"] = slab_info.get("critical_path")
@@ -616,6 +628,9 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (diagnostic runs only)")
+    ap.add_argument("--order", default="input", choices=["input", "cell", "random"],
+                    help="diagnostic (N = 1): reorder the particle set on the device before the run -- 'cell' = sorted by mesh "
+                         "cell (z fastest), 'random' = shuffled; the golden check still applies (P(k) does not depend on order)")
     ap.add_argument("--no-routing-stress", action="store_true", help="N > 1: skip the unsorted-input run after the timed region")
     args = ap.parse_args()
     # whole-run watchdog: a dead-lock (collectives, device-side barriers) must not hold the GPUs for long

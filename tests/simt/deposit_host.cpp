@@ -33,13 +33,8 @@ template <int S, typename PT, bool SOA, bool MASS, bool PAIR>
 void run(const void *p0, const void *p1, const void *p2, const void *mass, int mass_f64, long long np,
          const DepositGeom &G, float *mesh, float *mesh1, int num_sms) {
     using VT = typename std::conditional<MASS, P4, P3>::type;
-    const BrickGrid B = make_brick_grid(G, S);
-    DepositGeom G1 = G;
-    if (PAIR) {
-        G1.shift = G.shift + 0.5;
-        if (G.t32 >= 0.f) G1.t32 = G.t32 + 0.5f;
-    }
-    std::vector<VT> vals((size_t)np * (PAIR ? 2 : 1) + 1);
+    const BrickGrid B = make_brick_grid(G, S, PAIR);
+    std::vector<VT> vals((size_t)np + 1);
     std::vector<unsigned int> counts(B.nbricks + 2, 0u), start(B.nbricks + 2, 0xdeadbeefu), cursor(B.nbricks + 2, 0xdeadbeefu),
         filled(B.nbricks + 2, 0xdeadbeefu);
     const int nseg = (B.nbricks + SCAN_SEG - 1) / SCAN_SEG;
@@ -49,7 +44,7 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     const int pb = (int)std::min<long long>((np + tile - 1) / tile, (long long)num_sms * 8);
     simt::launch(pb, PART_THREADS, [&] {
-        brick_count_kernel<S, PT, SOA, PAIR>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, G1, B, counts.data());
+        brick_count_kernel<S, PT, SOA>((const PT *)p0, (const PT *)p1, (const PT *)p2, np, G, B, counts.data());
     });
     simt::launch(nseg, 1024, [&] { brick_segsum_kernel(counts.data(), B.nbricks, seg_total.data(), seg_filled.data()); });
     simt::launch(nseg, 1024, [&] {
@@ -57,15 +52,15 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
                           filled.data(), counter + 1);
     });
     simt::launch(pb, PART_THREADS, [&] {
-        brick_scatter_kernel<S, PT, SOA, MASS, PAIR, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
-                                                        G1, B, cursor.data(), vals.data());
+        brick_scatter_kernel<S, PT, SOA, MASS, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
+                                                  B, cursor.data(), vals.data());
     });
     simt::launch(B.nbricks, TILE_THREADS, [&] {
-        brick_tile_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, PAIR ? 0 : -1);
+        brick_tile_kernel<S, MASS, PAIR, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh, 0);
     });
     if (PAIR)
         simt::launch(B.nbricks, TILE_THREADS, [&] {
-            brick_tile_kernel<S, MASS, VT>(vals.data(), start.data(), filled.data(), counter + 1, G1, B, mesh1, 1);
+            brick_tile_kernel<S, MASS, PAIR, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh1, 1);
         });
 }
 
@@ -104,23 +99,18 @@ extern "C" long long simt_deposit_sorted(const void *p0, const void *p1, const v
 }
 
 
-// brick_keys for every particle (float32 positions, whole-mesh plan): keys, brick-local coordinates and the split
-// flag of the interlaced pair, for a direct check of the float-register index arithmetic at large mesh sizes.
-extern "C" void simt_brick_keys(const float *xyz, long long np, int N, double pos_scale, int resampler,
-                                unsigned int *key0, unsigned int *key1, float *l0, float *l1, int *split, int *grid) {
+// brick_keys for every particle (float32 positions, whole-mesh plan): key and brick-local coordinates, for a direct
+// check of the float-register index arithmetic at large mesh sizes.  pair: the interlaced pair's brick grid.
+extern "C" void simt_brick_keys(const float *xyz, long long np, int N, double pos_scale, int resampler, int pair,
+                                unsigned int *key, float *l, int *grid) {
     const DepositGeom G = make_geom(N, pos_scale, 0.0, resampler, 0, N, 1, 2);
-    DepositGeom G1 = G;
-    G1.shift = 0.5;
-    G1.t32 = G.t32 + 0.5f;
     const int S = resampler == APK_CIC ? 2 : 3;
-    const BrickGrid B = make_brick_grid(G, S);
-    grid[0] = B.nbx; grid[1] = B.nby; grid[2] = B.nbz;
+    const BrickGrid B = make_brick_grid(G, S, pair != 0);
+    grid[0] = B.nbx; grid[1] = B.nby; grid[2] = B.nbz; grid[3] = B.zcells;
     for (long long p = 0; p < np; ++p) {
-        float a[3], b[3];
-        bool sp;
-        if (S == 2) brick_keys<2, float, true>(xyz + 3 * p, G, G1, B, key0[p], a, key1[p], b, sp);
-        else brick_keys<3, float, true>(xyz + 3 * p, G, G1, B, key0[p], a, key1[p], b, sp);
-        for (int d = 0; d < 3; ++d) { l0[3 * p + d] = a[d]; l1[3 * p + d] = b[d]; }
-        split[p] = sp;
+        float a[3];
+        if (S == 2) brick_keys<2, float>(xyz + 3 * p, G, B, key[p], a);
+        else brick_keys<3, float>(xyz + 3 * p, G, B, key[p], a);
+        for (int d = 0; d < 3; ++d) l[3 * p + d] = a[d];
     }
 }

@@ -208,6 +208,7 @@ inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(__fmul_rn(a.x,
 inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
 inline int __float2int_rn(float f) { return (int)std::nearbyintf(f); }      // round to nearest even, like cvt.rni
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
 inline int __double2loint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i & 0xffffffffll); }
 inline int __double2hiint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i >> 32); }

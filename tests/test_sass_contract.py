@@ -40,29 +40,30 @@ def count(ops, prefix):
 
 
 def test_tsc_tile_kernel_is_integer_shared_atomics_plus_reds(sass):
-    ops = one(sass, r"brick_tile_kernelILi3ELb0ENS_2P3")
-    assert count(ops, "ATOMS.ADD") >= 27             # one native integer shared-memory atomic per window cell
+    ops = one(sass, r"brick_tile_kernelILi3ELb0ELb1ENS_2P3")        # TSC, unit masses, interlaced pair
+    assert count(ops, "ATOMS.ADD") == 27             # one native integer shared-memory atomic per window cell
     assert not any(op.startswith("ATOMS.CAS") for op in ops), "shared-memory CAS loop (float atomic) in the tile kernel"
-    assert count(ops, "F2I") <= 8                    # weights become fixed point through the FFMA magic constant, not F2I
-    assert count(ops, "FFMA") >= 27
+    assert count(ops, "F2I") <= 8                    # the weight's subnormal bit pattern IS the fixed-point value: no F2I,
+    assert 36 <= count(ops, "FMUL") <= 70            # ... one FMUL per cell (27 + 9 pair products + the axis weights)
+    assert not any(op.startswith("FMUL") and ".FTZ" in op for op in ops), "flush-to-zero would zero every weight"
     assert count(ops, "REDG") >= 1 and count(ops, "ATOMG") == 0      # flush: fire-and-forget float REDs
     assert count(ops, "LDL") + count(ops, "STL") == 0, "the TSC tile kernel spills"
     assert count(ops, "BAR") <= 6
 
 
 def test_cic_and_mass_tile_kernels(sass):
-    ops = one(sass, r"brick_tile_kernelILi2ELb0ENS_2P3")
+    ops = one(sass, r"brick_tile_kernelILi2ELb0ELb0ENS_2P3")
     assert count(ops, "ATOMS.ADD") >= 8 and not any(op.startswith("ATOMS.CAS") for op in ops)
-    ops = one(sass, r"brick_tile_kernelILi3ELb1ENS_2P4")
+    ops = one(sass, r"brick_tile_kernelILi3ELb1ELb0ENS_2P4")
     assert count(ops, "ATOMS.ADD") >= 27 and not any(op.startswith("ATOMS.CAS") for op in ops)
     assert count(ops, "F2I") >= 27                   # with masses: FMUL + F2I at the chunk's own scale
     assert count(ops, "LDL") + count(ops, "STL") == 0
 
 
 def test_partition_counts_with_reds_and_scatters_with_returning_atomics(sass):
-    cnt = one(sass, r"brick_count_kernelILi3EfLb1ELb1")          # TSC, float32, SoA, interlaced pair
+    cnt = one(sass, r"brick_count_kernelILi3EfLb1E")             # TSC, float32, SoA
     assert count(cnt, "REDG") >= 4 and count(cnt, "ATOMG") == 0
-    sc = one(sass, r"brick_scatter_kernelILi3EfLb1ELb0ELb1")
+    sc = one(sass, r"brick_scatter_kernelILi3EfLb1ELb0E")
     assert count(sc, "ATOMG") >= 4 and count(sc, "STG") >= 12
 
 

@@ -112,9 +112,9 @@ def test_slab_plan_ignores_foreign_particles(simt, oracle_fast):
 @pytest.mark.parametrize("resampler", ["cic", "tsc"])
 @pytest.mark.parametrize("N,f64", [(6, True), (12, False), (30, False)])
 def test_twin_wrapping_inside_one_brick(simt, oracle_fast, resampler, N, f64):
-    """N <= 30: a single brick spans z (N <= 12 / 6: x / y too), so the shifted twin of a particle in the last cell
-    wraps around the box inside the same brick and must still get a copy of its own (the randomised runs of this
-    harness found that the brick key alone missed it).  Positions include exact cell and half-cell faces."""
+    """N <= 30: a single brick spans z (N <= 12 / 6: x / y too), so the tile's window wraps around the box onto
+    itself, and the shifted twin of a particle in the last cell has its home cell one past the brick's last one.
+    Positions include exact cell and half-cell faces."""
     rng = np.random.default_rng(40 + N)
     L = 7.3
     pos = np.concatenate([rng.random((2500, 3)) * 3 * L - L, rng.integers(0, 2 * N + 1, (800, 3)) * 0.5 * L / N])
@@ -125,47 +125,48 @@ def test_twin_wrapping_inside_one_brick(simt, oracle_fast, resampler, N, f64):
 
 
 @pytest.mark.parametrize("resampler", ["cic", "tsc"])
+@pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("N", [1024, 2048, 1000])
-def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, N):
+def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, pair, N):
     """The partition's index arithmetic stays in float32 registers (cells up to 2047, bricks up to 341, no integer
-    division): checked for every particle against integer arithmetic on the float64 grid coordinate -- home cell,
-    brick, brick-local coordinate of both interlaced twins and the rule for the twin's own copy."""
+    division, no conversion): checked for every particle against integer arithmetic on the float64 grid coordinate.
+    Away from cell faces the key is the brick of the mesh-0 home cell and the payload its coordinate in that brick;
+    AT a face (within rounding) either neighbour is allowed, but key and payload must still name the same point."""
     rng = np.random.default_rng(N)
     n = 200000
     pos = rng.random((n, 3))
     pos[:20000] = rng.integers(0, 2 * N, (20000, 3)) * (0.5 / N) + rng.normal(0, 1e-5, (20000, 3))   # around cell faces
     pos[20000:22000] = rng.random((2000, 3)) * 3 - 1                                               # outside the box
+    pos[22000:22100] = rng.integers(0, 2 * N + 1, (100, 3)) * (0.5 / N)                            # exactly on faces
     pos = pos.astype(np.float32)
     simt.simt_brick_keys.restype = None
-    simt.simt_brick_keys.argtypes = [ct.c_void_p, ct.c_longlong, ct.c_int, ct.c_double, ct.c_int] + [ct.c_void_p] * 6
-    key0, key1 = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
-    l0, l1 = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32)
-    split, grid = np.zeros(n, np.int32), np.zeros(3, np.int32)
-    simt.simt_brick_keys(pos.ctypes.data, n, N, 1.0, {"cic": 2, "tsc": 3}[resampler], key0.ctypes.data, key1.ctypes.data,
-                         l0.ctypes.data, l1.ctypes.data, split.ctypes.data, grid.ctypes.data)
-    edge = np.array([12, 6, 30 if resampler == "tsc" else 31])
+    simt.simt_brick_keys.argtypes = [ct.c_void_p, ct.c_longlong, ct.c_int, ct.c_double, ct.c_int, ct.c_int] + [ct.c_void_p] * 3
+    key = np.zeros(n, np.uint32)
+    l = np.zeros((n, 3), np.float32)
+    grid = np.zeros(4, np.int32)
+    simt.simt_brick_keys(pos.ctypes.data, n, N, 1.0, {"cic": 2, "tsc": 3}[resampler], pair, key.ctypes.data,
+                         l.ctypes.data, grid.ctypes.data)
+    zc = 32 - ({"cic": 1, "tsc": 2}[resampler]) - pair
+    assert grid[3] == zc
+    edge = np.array([12, 6, zc])
     g = pos.astype(np.float64) * N                               # pos_scale = 1: Ramses-style coordinates
-    clear = np.abs(g * 2 - np.round(g * 2)).min(axis=1) > 1e-9   # not within rounding of a cell / half-cell face
     round_up = 0.5 if resampler == "tsc" else 0.0
-
-    def expect(shift):
-        home = np.floor(g + shift + round_up).astype(np.int64)
-        frac = g + shift - home                                   # relative to the home cell
-        cell = home % N
-        brick = cell // edge
-        key = (brick[:, 0] * grid[1] + brick[:, 1]) * grid[2] + brick[:, 2]
-        return key, cell - brick * edge + frac, cell, brick
-
-    k0, c0, cell0, b0 = expect(0.0)
-    k1, c1, cell1, b1 = expect(0.5)
-    np.testing.assert_array_equal(key0[clear], k0[clear])
-    np.testing.assert_array_equal(key1[clear], k1[clear])
-    np.testing.assert_allclose(l0[clear], c0[clear], rtol=0, atol=3e-4)      # float32 positions at |g| ~ 2000
-    np.testing.assert_allclose(l1[clear], c1[clear], rtol=0, atol=3e-4)
-    # the twin shares mesh 0's copy exactly when it sits in the same brick at mesh 0's coordinate + half a cell
-    own_copy = (k1 != k0) | (np.abs(c1 - c0 - 0.5) > 0.25).any(axis=1)
-    np.testing.assert_array_equal(split[clear].astype(bool), own_copy[clear])
-    assert split.mean() < 0.25
+    home = np.floor(g + round_up).astype(np.int64)
+    cell = home % N
+    brick = cell // edge
+    want_key = (brick[:, 0] * grid[1] + brick[:, 1]) * grid[2] + brick[:, 2]
+    want_l = cell - brick * edge + (g - home)                    # TSC: home + [-0.5, 0.5);  CIC: home + [0, 1)
+    clear = np.abs(g + round_up - np.round(g + round_up)).min(axis=1) > 1e-3   # not within rounding of a face of the home cell
+    np.testing.assert_array_equal(key[clear], want_key[clear])
+    np.testing.assert_allclose(l[clear], want_l[clear], rtol=0, atol=3e-4)      # float32 positions at |g| ~ 2000
+    # every particle, faces included: brick origin + payload is the particle's grid coordinate (mod N)
+    kb = np.stack([key // (grid[1] * grid[2]), (key // grid[2]) % grid[1], key % grid[2]], axis=1).astype(np.int64)
+    back = kb * edge + l.astype(np.float64)
+    diff = (back - g + N / 2) % N - N / 2
+    assert np.abs(diff).max() < 3e-4
+    lo, hi = (-0.5, edge - 0.5) if resampler == "tsc" else (0.0, edge)
+    assert (l >= lo - 3e-4).all() and (l <= hi + 3e-4).all()
+    assert (kb < grid[:3]).all()
 
 
 def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):

@@ -11,7 +11,7 @@ constexpr int THREADS = 256;
 constexpr int ITERS = 2048;
 constexpr int UPD = 27;
 
-enum Mode { DISTINCT_BANKS = 0, RANDOM_ADDR = 1, JITTERED_Z = 2, SAME_ADDR = 3 };
+enum Mode { DISTINCT_BANKS = 0, RANDOM_ADDR = 1, JITTERED_Z = 2, SAME_ADDR = 3, DUP2 = 4, DUP4 = 5, CONF2 = 6, CONF4 = 7 };
 
 __device__ __forceinline__ unsigned lcg(unsigned &s) { s = s * 1664525u + 1013904223u; return s; }
 
@@ -24,6 +24,10 @@ __device__ __forceinline__ int base_addr(int lane, int warp, int it, unsigned &r
         const int z = (lane + (int)((lcg(rng) >> 20) % 4) - 1) & 31;
         return ((it * 13 + warp) % 60) * 32 + z;
     }
+    if (MODE == DUP2) return ((it * 37 + warp * 5) & 63) * 32 + (((lane >> 1) + it) & 31);        // 16 addresses, 2 lanes each
+    if (MODE == DUP4) return ((it * 37 + warp * 5) & 63) * 32 + (((lane >> 2) + it) & 31);        // 8 addresses, 4 lanes each
+    if (MODE == CONF2) return (((it * 37 + warp * 5) & 31) * 2 + (lane & 1)) * 32 + (((lane >> 1) + it) & 31);   // 2 addresses per bank
+    if (MODE == CONF4) return (((it * 37 + warp * 5) & 15) * 4 + (lane & 3)) * 32 + (((lane >> 2) + it) & 31);   // 4 addresses per bank
     return 17;
 }
 
@@ -132,6 +136,10 @@ int main() {
         run("ATOMS.ADD u32 random cells", [](int g, void *o, long long *c) { k_atoms<RANDOM_ADDR, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
         run("ATOMS.ADD u32 jittered z-line", [](int g, void *o, long long *c) { k_atoms<JITTERED_Z, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
         run("ATOMS.ADD u32 one address", [](int g, void *o, long long *c) { k_atoms<SAME_ADDR, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
+        run("ATOMS.ADD u32 2 lanes per address", [](int g, void *o, long long *c) { k_atoms<DUP2, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
+        run("ATOMS.ADD u32 4 lanes per address", [](int g, void *o, long long *c) { k_atoms<DUP4, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
+        run("ATOMS.ADD u32 2 addresses per bank", [](int g, void *o, long long *c) { k_atoms<CONF2, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
+        run("ATOMS.ADD u32 4 addresses per bank", [](int g, void *o, long long *c) { k_atoms<CONF4, unsigned><<<g, THREADS>>>((unsigned *)o, c); }, c, sms);
         run("ATOMS.ADD u64 distinct banks", [](int g, void *o, long long *c) { k_atoms<DISTINCT_BANKS, unsigned long long><<<g, THREADS>>>((unsigned long long *)o, c); }, c, sms);
         run("ATOMS.ADD u64 random cells", [](int g, void *o, long long *c) { k_atoms<RANDOM_ADDR, unsigned long long><<<g, THREADS>>>((unsigned long long *)o, c); }, c, sms);
         run("atomicAdd f32 (CAS loop?) distinct banks", [](int g, void *o, long long *c) { k_atoms<DISTINCT_BANKS, float><<<g, THREADS>>>((float *)o, c); }, c, sms);
