@@ -131,7 +131,6 @@ int apk_plan_destroy(apk_plan *P) {
     if (P->has_fft1d) cufftDestroy(P->fft1d);
     if (P->scratch) cudaFree(P->scratch);
     if (P->ev_ready) for (auto &e : P->ev) cudaEventDestroy(e);
-    if (P->aux_stream) { cudaStreamDestroy(P->aux_stream); cudaEventDestroy(P->zero_begin); cudaEventDestroy(P->zero_done); }
     delete P;
     return 0;
 }
@@ -190,33 +189,18 @@ static int deposit_impl(apk_plan *P, const void *p0, const void *p1, const void 
     };
     const DepositGeom G = geom(shift);
     const size_t mesh_bytes = sizeof(float) * (size_t)G.nplanes * P->N * P->ldz;
+    if (zero_first) {
+        APK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, st));
+        if (mesh1) APK_CUDA(cudaMemsetAsync(mesh1, 0, mesh_bytes, st));
+    }
     if (method == APK_DEPOSIT_AUTO) {
         // the sorted path pays per brick (a tile to clear and to flush): it wins once the bricks are populated --
         // more than ~16 particles per brick of ~2200 cells -- and the set is large enough to amortise its launches
         const double bricks = (double)G.nplanes * P->N * P->N / 2160.0;
         method = (np >= (1 << 18) && (double)np >= 16.0 * bricks) ? APK_DEPOSIT_SORTED : APK_DEPOSIT_ATOMIC;
     }
-    const bool sorted = method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0;
-    if (zero_first && sorted && np >= (1 << 22)) {
-        // large sorted deposit: the partition kernels (10 ms at 1024^3, DRAM half busy) do not touch the mesh, so the
-        // clear runs beside them on the plan's own stream; run_sorted makes the tile kernel wait for it
-        if (!P->aux_stream) {
-            APK_CUDA(cudaStreamCreateWithFlags(&P->aux_stream, cudaStreamNonBlocking));
-            APK_CUDA(cudaEventCreateWithFlags(&P->zero_begin, cudaEventDisableTiming));
-            APK_CUDA(cudaEventCreateWithFlags(&P->zero_done, cudaEventDisableTiming));
-        }
-        APK_CUDA(cudaEventRecord(P->zero_begin, st));                    // whatever used the meshes before, on st
-        APK_CUDA(cudaStreamWaitEvent(P->aux_stream, P->zero_begin, 0));
-        APK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, P->aux_stream));
-        if (mesh1) APK_CUDA(cudaMemsetAsync(mesh1, 0, mesh_bytes, P->aux_stream));
-        APK_CUDA(cudaEventRecord(P->zero_done, P->aux_stream));
-        P->zero_pending = true;
-    } else if (zero_first) {
-        APK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, st));
-        if (mesh1) APK_CUDA(cudaMemsetAsync(mesh1, 0, mesh_bytes, st));
-    }
     if (P->timing) P->dep_timed = false;            // an untimed call leaves the last timed deposit's events alone
-    if (sorted)
+    if (method == APK_DEPOSIT_SORTED && resampler != APK_NGP && np > 0)
         return deposit_sorted_launch(P, p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, mesh1, st);
     if (P->mark(3, st)) { set_error("apk_deposit: event record failed"); return 1; }
     int rc = deposit_atomic_launch(p0, p1, p2, layout, pos_dtype, mass, mass_dtype, np, resampler, G, mesh, P->num_sms, st);

@@ -64,11 +64,6 @@ struct apk_plan {
     size_t fft_work_bytes = 0;  // sum of fft_ws
     size_t fft_ws[3] = {0, 0, 0};   // cuFFT work areas (3-D, 2-D, 1-D plan), 256-byte multiples, at the tail of the workspace
     cudaEvent_t first_mesh_event = nullptr;   // apk_plan_set_first_mesh_event
-    // the sorted deposit clears the mesh(es) on a plan-owned stream WHILE the partition kernels run (they do not touch
-    // the mesh); the tile kernel waits for zero_done
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t zero_begin = nullptr, zero_done = nullptr;
-    bool zero_pending = false;
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
     double *scratch = nullptr;   // small device scratch for reductions (plan-owned)

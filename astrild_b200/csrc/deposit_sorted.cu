@@ -27,8 +27,6 @@
 //      twin's boundary particles twice with sign flags (14 % more payload, ~110 more instructions per particle in
 //      each partition pass).
 #include "brick_common.cuh"
-#include <cstdlib>
-#include <string>
 #include <algorithm>
 #include <cstdint>
 #include <type_traits>
@@ -210,9 +208,12 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 //   Integer adds commute: a brick's contribution to the mesh does not depend on the order in which the partition
 //   filed its particles.
 //   The tile goes to the mesh as one coalesced 128-byte RED.ADD.F32 per (x,y) column, zeros skipped.
-#ifndef APK_TILE_DEFAULT_QUEUE
-#define APK_TILE_DEFAULT_QUEUE 0
-#endif
+//   A conflict-free variant was built and measured (round 2, commit "Experiment: bank-queue tile kernel"): tile skewed so
+//   that bank = (11 x + 5 y + z) mod 32, each chunk counting-sorted in shared memory into 32 queues by the bank of the
+//   window's first cell, lane L working through queue L -- every ATOMS then hits 32 different banks.  Correct, but
+//   28.8 against 24.0 ms for both meshes at 1024^3: the sort's own shared-memory traffic (a returning ATOMS, three
+//   scattered STS and LDS per particle), its five barriers per chunk and the idle lanes of the shorter queues
+//   (utilisation 0.72) cost more than the conflicts.  Removed.
 #ifndef APK_TILE_FLUSH
 #define APK_TILE_FLUSH 4095
 #endif
@@ -403,244 +404,10 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Tile kernel, BANK-QUEUE variant.  The particle-parallel kernel above is bound by the shared-memory pipe: the 32
-// lanes of an ATOMS hit random banks, 3.3 wavefronts per instruction.  Here the tile is laid out skewed,
-//     word(x, y, z) = x * SX + y * SY + z,   SY = 32 + 5,   SX = 11 (mod 32),   bank = (11 x + 5 y + z) mod 32,
-// each chunk of <= QCHUNK particles is counting-sorted IN SHARED MEMORY into 32 queues by the bank q of the window's
-// first cell, and lane L then deposits only particles of queue L: at every one of the S^3 instructions lane L hits
-// bank (L + 11 a + 5 b + c) mod 32 -- 32 different banks, one wavefront, for ANY particle order.  The price is idle
-// lanes where queues are shorter than the longest one (utilisation ~0.7 at one particle per cell: the hash spreads a
-// brick's ~2100 particles over the queues like a Poisson draw) and the in-chunk sort (one returning ATOMS, three
-// scattered STS and three LDS per particle).
-//   A  every thread loads its QK particles into registers, finds the home cell, takes a rank in its queue
-//   B  warp 0 scans the 32 queue lengths
-//   C  registers -> staging arrays at queue start + rank
-//   D  warp w, lane L: entries w, w + 8, ... of queue L; next entry's LDS in flight during the S^3 ATOMS
-//   E  flush as above (columns are contiguous in the skewed layout too)
-#ifndef APK_QTILE_CTAS
-#define APK_QTILE_CTAS 4
-#endif
-constexpr int QK = 9, QCHUNK = QK * TILE_THREADS;     // particles per chunk = per flush
-template <int S, bool PAIR> struct QTile {
-    static constexpr int OFF = (S == 3) ? 1 : 0;
-    static constexpr int TX = BX + S - 1 + (PAIR ? 1 : 0), TY = BY + S - 1 + (PAIR ? 1 : 0);
-    static constexpr int SY = 37;
-    static constexpr int SX = ((TY * SY - 11 + 31) / 32) * 32 + 11;      // >= TY * SY: rows never overlap
-    static constexpr int WORDS = ((TX * SX + 3) / 4) * 4;
-};
-template <int S, bool MASS, bool PAIR> constexpr size_t qtile_smem_bytes() {
-    return 4 * ((size_t)QTile<S, PAIR>::WORDS + (size_t)(MASS ? 4 : 3) * QCHUNK);
-}
-
-template <int S, bool MASS, bool PAIR, typename VT>
-__global__ void __launch_bounds__(TILE_THREADS, APK_QTILE_CTAS)
-brick_tileq_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
-                   const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
-                   DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
-    using T = QTile<S, PAIR>;
-    constexpr int ZC = BrickZ<S, PAIR>::CELLS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned int *tile = reinterpret_cast<unsigned int *>(smem_raw);
-    float *sx = reinterpret_cast<float *>(tile + T::WORDS), *sy = sx + QCHUNK, *sz = sy + QCHUNK, *sm = sz + QCHUNK;
-    __shared__ unsigned int qcount[32], qstart[32], qmax;
-    __shared__ long long xoff[T::TX];
-    __shared__ int yoff[T::TY];
-    __shared__ float red_s[2 * (TILE_THREADS / 32)];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float twin = sel > 0 ? 0.5f : 0.f;
-    const float lastx = (float)(BX - 1 + (sel > 0)), lasty = (float)(BY - 1 + (sel > 0)), lastz = (float)(ZC - 1 + (sel > 0));
-
-    const unsigned int nfilled = *nfilled_ptr;
-    for (unsigned int slot = blockIdx.x; slot < nfilled; slot += gridDim.x) {
-        const unsigned int brick = filled[slot];
-        const unsigned int pbeg = brick_start[brick], pend = brick_start[brick + 1];
-        const int bz = brick % B.nbz;
-        const int by = (brick / B.nbz) % B.nby;
-        const int bx = brick / (B.nbz * B.nby);
-
-        __syncthreads();                              // (persistent grids) the previous brick's flush is complete
-        for (int i = tid; i < T::WORDS / 4; i += TILE_THREADS) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < T::TX) {
-            int px = bx * BX - T::OFF + tid;
-            bool ok = true;
-            if (G.slab) ok = px >= 0 && px < G.nplanes;
-            else px = wrap_index32(px, G.N);
-            xoff[tid] = ok ? (long long)px * G.N * G.ldz : -1LL;
-        } else if (tid < T::TX + T::TY) {
-            yoff[tid - T::TX] = wrap_index32(by * BY - T::OFF + tid - T::TX, G.N) * G.ldz;
-        }
-
-        for (unsigned int c0 = pbeg; c0 < pend; c0 += QCHUNK) {
-            const unsigned int c1 = min(c0 + (unsigned int)QCHUNK, pend);
-            if (tid < 32) qcount[tid] = 0u;
-            __syncthreads();                          // tile cleared / previous chunk flushed, counters zero
-
-            // ---- A: particles -> registers, home cell -> queue (bank of the window's first cell), rank in the queue ----
-            float px[QK], py[QK], pz[QK], pm[QK];
-            unsigned int code[QK];                    // rank << 5 | queue
-            float top = 0.f, sum = 0.f;
-#pragma unroll
-            for (int k = 0; k < QK; ++k) {
-                const unsigned int p = c0 + tid + k * TILE_THREADS;
-                code[k] = 0xffffffffu;
-                px[k] = py[k] = pz[k] = pm[k] = 0.f;
-                if (p < c1) {
-                    const VT v = vals[p];
-                    px[k] = v.x + twin; py[k] = v.y + twin; pz[k] = v.z + twin;
-                    float d;
-                    int hx, hy, hz;
-                    tile_home<S>(px[k], lastx, d, hx);
-                    tile_home<S>(py[k], lasty, d, hy);
-                    tile_home<S>(pz[k], lastz, d, hz);
-                    const unsigned int q = (unsigned int)(hx * T::SX + hy * T::SY + hz) & 31u;
-                    code[k] = (atomicAdd(&qcount[q], 1u) << 5) | q;
-                    if constexpr (MASS) {
-                        pm[k] = v.m;
-                        top = fmaxf(top, fabsf(v.m));
-                        sum += fabsf(v.m);
-                    }
-                }
-            }
-            if constexpr (MASS) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
-                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                }
-                if (lane == 0) { red_s[warp] = top; red_s[TILE_THREADS / 32 + warp] = sum; }
-            }
-            __syncthreads();
-
-            // ---- B: queue starts ----
-            if (warp == 0) {
-                const unsigned int n = qcount[lane];
-                unsigned int incl = n, mx = n;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                }
-                qstart[lane] = incl - n;
-                if (lane == 0) qmax = mx;
-            }
-            // masses: unit and fixed-point scale of the chunk, as in the kernel above
-            float unit = 1.f, inv_unit = 1.f, mscale = 1.f;
-            int frac_bits = 0;
-            if constexpr (MASS) {
-                top = red_s[0]; sum = red_s[TILE_THREADS / 32];
-#pragma unroll
-                for (int i = 1; i < TILE_THREADS / 32; ++i) { top = fmaxf(top, red_s[i]); sum += red_s[TILE_THREADS / 32 + i]; }
-                int e = ((__float_as_int(top) >> 23) & 0xff) + ((__float_as_int(top) & 0x7fffff) ? 1 : 0);
-                e = min(max(e, 2), 252);
-                unit = __int_as_float(e << 23);
-                inv_unit = __int_as_float((254 - e) << 23);
-                if (!(top > 0.f) || !(sum < 3.0e38f)) { unit = 1.f; inv_unit = 0.f; sum = 1.f; }
-                constexpr float WMAX = (S == 3) ? 0.43f : 1.001f;
-                const float room = 2147483648.f / (WMAX * fmaxf(sum * inv_unit, 1.f));
-                frac_bits = min(((__float_as_int(room) >> 23) & 0xff) - 127, 30);
-                mscale = __int_as_float((127 + frac_bits) << 23);
-            } else {
-                frac_bits = tile_frac_bits<S>((int)(c1 - c0));
-            }
-            const float quantum = __int_as_float((127 - frac_bits) << 23) * unit;
-            const float KXY = MASS ? 1.f : __int_as_float((127 - 40) << 23);
-            const float KZ = MASS ? 1.f : __int_as_float((127 + frac_bits - 69) << 23);
-            __syncthreads();
-
-            // ---- C: registers -> staging, queue by queue ----
-#pragma unroll
-            for (int k = 0; k < QK; ++k)
-                if (code[k] != 0xffffffffu) {
-                    const unsigned int s = qstart[code[k] & 31u] + (code[k] >> 5);
-                    sx[s] = px[k]; sy[s] = py[k]; sz[s] = pz[k];
-                    if constexpr (MASS) sm[s] = pm[k];
-                }
-            __syncthreads();
-
-            // ---- D: lane L works through queue L ----
-            {
-                const unsigned int len = qcount[lane], base = qstart[lane], maxl = qmax;
-                unsigned int i = warp;
-                float nx = 0.f, ny = 0.f, nz = 0.f, nm = 0.f;
-                bool act = i < len;
-                if (act) { nx = sx[base + i]; ny = sy[base + i]; nz = sz[base + i]; if constexpr (MASS) nm = sm[base + i]; }
-                for (; i < maxl; i += TILE_THREADS / 32) {
-                    const float x = nx, y = ny, z = nz, m = nm;
-                    const bool cur = act;
-                    const unsigned int j = i + TILE_THREADS / 32;
-                    act = j < len;
-                    if (act) { nx = sx[base + j]; ny = sy[base + j]; nz = sz[base + j]; if constexpr (MASS) nm = sm[base + j]; }
-                    if (!cur) continue;
-                    float dx, dy, dz;
-                    int hx, hy, hz;
-                    tile_home<S>(x, lastx, dx, hx);
-                    tile_home<S>(y, lasty, dy, hy);
-                    tile_home<S>(z, lastz, dz, hz);
-                    float kz = KZ;
-                    if constexpr (MASS) kz = (m * inv_unit) * mscale;
-                    float wx[S], wy[S], wz[S];
-                    if (S == 2) {
-                        wx[S - 1] = dx * KXY; wx[0] = KXY - wx[S - 1];
-                        wy[S - 1] = dy * KXY; wy[0] = KXY - wy[S - 1];
-                        wz[S - 1] = dz * kz;  wz[0] = kz - wz[S - 1];
-                    } else {
-                        const float ax = 0.5f - dx, cx = 0.5f + dx, ay = 0.5f - dy, cy = 0.5f + dy, az = 0.5f - dz, cz = 0.5f + dz;
-                        const float hxy = 0.5f * KXY, hz2 = 0.5f * kz;
-                        wx[0] = (ax * hxy) * ax; wx[S / 2] = fmaf(-dx, dx, 0.75f) * KXY; wx[S - 1] = (cx * hxy) * cx;
-                        wy[0] = (ay * hxy) * ay; wy[S / 2] = fmaf(-dy, dy, 0.75f) * KXY; wy[S - 1] = (cy * hxy) * cy;
-                        wz[0] = (az * hz2) * az; wz[S / 2] = fmaf(-dz, dz, 0.75f) * kz;  wz[S - 1] = (cz * hz2) * cz;
-                    }
-                    unsigned int *cell = tile + hx * T::SX + hy * T::SY + hz;
-#pragma unroll
-                    for (int a = 0; a < S; ++a)
-#pragma unroll
-                        for (int b = 0; b < S; ++b) {
-                            const float wxy = wx[a] * wy[b];
-#pragma unroll
-                            for (int c = 0; c < S; ++c) {
-                                const unsigned int fx = MASS ? (unsigned int)__float2int_rn(wxy * wz[c])
-                                                             : __float_as_uint(__fmul_rn(wxy, wz[c]));
-                                atomicAdd(cell + a * T::SX + b * T::SY + c, fx);
-                            }
-                        }
-                }
-            }
-            __syncthreads();   // queue variant: all deposits of the chunk are in the tile
-
-            // ---- E: tile -> mesh ----
-            float *mz = mesh + wrap_index32(bz * ZC - T::OFF + lane, G.N);
-            const bool more = c1 < pend;
-            for (int col = warp; col < T::TX * T::TY; col += TILE_THREADS / 32) {
-                const int u = col / T::TY, w = col - u * T::TY;
-                const unsigned int fx = tile[u * T::SX + w * T::SY + lane];
-                if (more) tile[u * T::SX + w * T::SY + lane] = 0u;
-                const long long xo = xoff[u];
-                if (fx != 0u && xo >= 0) {
-                    const float val = MASS ? (float)(int)fx * quantum : (float)fx * quantum;
-                    atomicAdd(mz + xo + yoff[w], val);
-                }
-            }
-        }
-    }
-}
-
 static size_t max_bricks(const apk_plan *P) {
     return (size_t)((P->N + 3 + BX - 1) / BX) * ((P->N + BY - 1) / BY) * ((P->N + 28) / 29);
 }
 static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
-
-// APK_TILE=queue | pp selects the tile kernel (A/B runs); read once
-static bool tile_variant_is_queue() {
-    static const int v = [] {
-        const char *e = getenv("APK_TILE");
-        if (e && std::string(e) == "queue") return 1;
-        if (e && std::string(e) == "pp") return 0;
-        return APK_TILE_DEFAULT_QUEUE;
-    }();
-    return v != 0;
-}
 
 // pair: the interlaced twins share one partition and one payload -- no extra room needed
 size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int /*pair*/) {
@@ -693,20 +460,8 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
 
     // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
     const int ctas = B.nbricks;
-    const bool queues = tile_variant_is_queue();
-    auto kern = queues ? brick_tileq_kernel<S, MASS, PAIR, VT> : brick_tile_kernel<S, MASS, PAIR, VT>;
-    const size_t dyn = queues ? qtile_smem_bytes<S, MASS, PAIR>() : 0;
-    if (queues) {
-        static bool opted = false;                   // per instantiation; the attribute is per function and device-wide
-        if (!opted) {
-            APK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            opted = true;
-        }
-    }
-    if (P->zero_pending) {                          // the meshes are being cleared on the plan's stream (api.cu)
-        P->zero_pending = false;
-        APK_CUDA(cudaStreamWaitEvent(st, P->zero_done, 0));
-    }
+    auto kern = brick_tile_kernel<S, MASS, PAIR, VT>;
+    const size_t dyn = 0;
     P->mark(3, st);
     kern<<<ctas, TILE_THREADS, dyn, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, 0);
     APK_CUDA(cudaGetLastError());

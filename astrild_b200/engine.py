@@ -225,43 +225,6 @@ class PkEngine:
         del keep
         return m0, m1
 
-    def deposit_pair_r2c(self, pos, mass=None, resampler: str = "tsc", pos_scale: float | None = None,
-                         method: str = "auto", out: tuple | None = None, deposit_done=None) -> tuple:
-        """deposit_pair followed by the r2c of both meshes -> (c0, c1), with mesh 0's transform OVERLAPPED with mesh 1's
-        tile kernel: the library records an event between the two tile kernels (apk_plan_set_first_mesh_event), a
-        high-priority side stream waits for it and runs cuFFT on mesh 0 (HBM-bound) while the main stream is still
-        depositing mesh 1 (bound by the shared-memory atomic pipe, DRAM a quarter busy); its CTAs take SMs as the tile
-        kernel's one-brick CTAs retire.  The transforms share one cuFFT plan and work area, so mesh 1's waits for mesh 0's.
-        deposit_done: optional timing torch.cuda.Event, recorded on the current stream when both meshes are deposited.
-        """
-        if self.n0 != self.N:
-            raise AstrildPkError("deposit_pair_r2c on a slab engine: use astrild_b200.distributed")
-        main = torch.cuda.current_stream(self.device)
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(self.device, priority=-1)
-        side = self._side
-        first = torch.cuda.Event()
-        first.record(main)                               # creates the handle; re-recorded inside the library
-        _lib.call("apk_plan_set_first_mesh_event", self._plan, ct.c_void_p(first.cuda_event))
-        try:
-            m0, m1 = self.deposit_pair(pos, mass, resampler, pos_scale, method, out=out)
-        finally:
-            _lib.call("apk_plan_set_first_mesh_event", self._plan, None)
-        if mass is not None and np.isscalar(mass) and float(mass) != 1.0:
-            first = torch.cuda.Event()                   # the scalar weight was applied after both tile kernels
-            first.record(main)
-        if deposit_done is not None:
-            deposit_done.record(main)
-        m0.record_stream(side)
-        done = torch.cuda.Event()
-        with torch.cuda.stream(side):
-            side.wait_event(first)
-            c0 = self.r2c(m0)
-            done.record(side)
-        main.wait_event(done)
-        c1 = self.r2c(m1)
-        return c0, c1
-
     def pow2_scaled(self, mass) -> tuple:
         """(mass / 2^e, 2^e) with 2^e the power of two nearest to max |mass| (exact scaling).  Masses in physical
         units (1e10..1e15) would put |field(k)|^2 near the float32 range in the binning kernel; the factor is

@@ -185,28 +185,17 @@ class CatalogMesh:
             if np.isfinite(top) and top > 0.0:
                 unit = 2.0 ** round(float(np.log2(top)))
                 w = wa * wa.dtype.type(1.0 / unit) if wa.dtype in (np.float32, np.float64) else wa.astype(np.float64) / unit
-        first = self._pos[0] if (isinstance(self._pos, (tuple, list)) and len(self._pos) == 3
-                                 and not np.isscalar(self._pos[0])) else self._pos
-        resident = isinstance(first, torch.Tensor) and first.is_cuda
-        if a["interlaced"] and resident and w is None:
-            # device-resident unit-mass particles: mesh 0's transform runs under mesh 1's tile kernel; the deposited
-            # mass is the particle count (every particle's window sums to one), so no reduction pass is needed
-            c, cs = eng.deposit_pair_r2c(self._pos, None, a["resampler"], self._pos_scale, self._method)
-            total = float(self._npart())
-        else:
-            meshes = eng.deposit_many(self._pos, w, a["resampler"], shifts, self._pos_scale, self._method)
-            mesh, mesh_s = meshes[0], (meshes[1] if a["interlaced"] else None)
-            total = eng.mesh_sum(mesh) if self._normalize else None
-            c = cs = None
+        meshes = eng.deposit_many(self._pos, w, a["resampler"], shifts, self._pos_scale, self._method)
+        mesh, mesh_s = meshes[0], (meshes[1] if a["interlaced"] else None)
+        total = eng.mesh_sum(mesh) if self._normalize else None
         if self._normalize:
             scale = eng.N ** 3 / total                # 1 + delta = mesh / mean: the unit cancels
         else:
             scale = unit / (eng.L / eng.N) ** 3
         # nbodykit CatalogMesh attrs: shotnoise = V * sum(w^2) / sum(w)^2  (= V / N unweighted)
         self.shotnoise = self._shotnoise()
-        if c is None:
-            c = eng.r2c(mesh)
-            cs = eng.r2c(mesh_s) if mesh_s is not None else None
+        c = eng.r2c(mesh)
+        cs = eng.r2c(mesh_s) if mesh_s is not None else None
         comp = (str(a["resampler"]).lower(), a["interlaced"]) if a["compensated"] else None
         return (c, cs), scale, comp
 

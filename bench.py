@@ -347,22 +347,16 @@ def run_ours(args, wl_key: str) -> None:
         def step(record=None):
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if record is not None else None
             if ev: ev[0].record()
-            piped = mesh2 is not None and not cross          # interlaced auto spectrum: mesh 0's r2c under mesh 1's tile kernel
-            if piped:
-                c1, c1s = eng.deposit_pair_r2c(pos, None, wl["resampler"], 1.0, "sorted", out=(mesh1, mesh2),
-                                               deposit_done=ev[1] if ev else None)
-            else:
-                deposit_field(pos, None, mesh1, mesh2, "sorted")
+            deposit_field(pos, None, mesh1, mesh2, "sorted")
             d1 = eng.last_deposit_ms() if record is not None else None
             s_first = s_matter
             if cross:                  # the halo catalogue: mass-weighted, small -> the library picks the direct-atomic path
                 hm, hfac = eng.pow2_scaled(halos[3])
                 deposit_field(halos[:3], hm, hmesh1, hmesh2, "auto")
                 s_first = N ** 3 / eng.mesh_sum(hmesh1)           # 1 + delta = mesh / mean: the power-of-two mass unit cancels
-            if ev and not piped: ev[1].record()
-            if not piped:
-                c1 = eng.r2c(mesh1)
-                c1s = eng.r2c(mesh2) if mesh2 is not None else None
+            if ev: ev[1].record()
+            c1 = eng.r2c(mesh1)
+            c1s = eng.r2c(mesh2) if mesh2 is not None else None
             h1 = eng.r2c(hmesh1) if cross else None
             h1s = eng.r2c(hmesh2) if hmesh2 is not None else None
             if ev: ev[2].record()
@@ -525,10 +519,7 @@ def run_ours(args, wl_key: str) -> None:
             "ms": {k: round(v, 4) for k, v in avg.items()},
             "deposit_stage_GBps": stage_bytes / (avg["deposit_stage"] * 1e-3) / 1e9,
             "deposit_stage_frac": stage_bytes / (avg["deposit_stage"] * 1e-3) / 1e9 / peak,
-            # interlaced auto spectrum: mesh 0's transform runs on a side stream under mesh 1's tile kernel, so "fft" is the
-            # EXPOSED transform time (mesh 1's, plus what is left of mesh 0's) and "deposit" includes the SM share it gave up
-            "fft_overlapped_with_deposit": bool(wl["interlaced"] and not cross),
-            "fft_GBps_algorithmic": None if (wl["interlaced"] and not cross) else fft_bytes / (avg["fft"] * 1e-3) / 1e9,
+            "fft_GBps_algorithmic": fft_bytes / (avg["fft"] * 1e-3) / 1e9,
             "bin_kernel_GBps": bin_bytes / (avg["bin_kernel"] * 1e-3) / 1e9,
             "bin_kernel_frac": bin_bytes / (avg["bin_kernel"] * 1e-3) / 1e9 / peak,
             "tile_kernel_GBps": dep_bytes / (dep_kernel_ms * 1e-3) / 1e9,

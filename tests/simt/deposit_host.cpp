@@ -14,8 +14,6 @@ using namespace apk;
 
 namespace {
 
-int g_tile_variant = 0;      // 0: particle-parallel tile kernel, 1: bank-queue variant
-
 
 DepositGeom make_geom(int N, double pos_scale, double shift, int resampler, int x0, int n0, int ghost_lo, int ghost_hi) {
     DepositGeom G;
@@ -57,13 +55,9 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
         brick_scatter_kernel<S, PT, SOA, MASS, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
                                                   B, cursor.data(), vals.data());
     });
-    static_assert(qtile_smem_bytes<S, MASS, PAIR>() <= simt::kDynSmem, "dynamic shared memory of the queue kernel");
     for (int sel = 0; sel < (PAIR ? 2 : 1); ++sel)
         simt::launch(B.nbricks, TILE_THREADS, [&] {
-            if (g_tile_variant)
-                brick_tileq_kernel<S, MASS, PAIR, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, sel ? mesh1 : mesh, sel);
-            else
-                brick_tile_kernel<S, MASS, PAIR, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, sel ? mesh1 : mesh, sel);
+            brick_tile_kernel<S, MASS, PAIR, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, sel ? mesh1 : mesh, sel);
         });
 }
 
@@ -79,8 +73,6 @@ void dispatch(const void *p0, const void *p1, const void *p2, const void *mass, 
 }
 
 }  // namespace
-
-extern "C" void simt_set_tile_variant(int v) { g_tile_variant = v; }
 
 // resampler: 2 = CIC, 3 = TSC.  mesh (and mesh1 for the interlaced pair) are float32 [nplanes][N][2 (N/2+1)],
 // accumulated into.  Slab plans: x0, n0 < N with ghost planes 1 below / 2 above.  Returns the fiber switches.

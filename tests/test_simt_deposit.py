@@ -25,13 +25,10 @@ def load(path):
     return lib
 
 
-@pytest.fixture(scope="module", params=["pp", "queue"])
-def simt(request):
-    """Both tile kernels run every test: the particle-parallel one and the bank-queue variant."""
+@pytest.fixture(scope="module")
+def simt():
     import build_simt
-    lib = load(build_simt.build())
-    lib.simt_set_tile_variant(int(request.param == "queue"))
-    return lib
+    return load(build_simt.build())
 
 
 def deposit(lib, pos, mass, N, L, resampler, pair=False, shift=0.0, soa=False, x0=0, n0=None):
