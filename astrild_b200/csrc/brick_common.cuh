@@ -83,7 +83,7 @@ __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const Dep
 //   g = x * scale is carried as p + e, p = fl(x * s0), e = the exact rounding error of p plus x * (s1 + s2)
 //     (scale = s0 + s1 + s2): an error-free product good to ~2^-70;
 //   anchor r = rint(p + shift') by the magic-constant add (ties irrelevant, see above); p - r is exact;
-//   periodic wrap by two compares (positions within one box length of the box; others -> false, float64 path);
+//   periodic wrap a mod N by one more rint (any |g| < 2^20; beyond that -> false, float64 path);
 //   brick b = rint((a + 0.5) / edge - 0.5) = floor((a + 0.5) / edge): the argument is never within 0.5 / edge of a tie;
 //   all indices are small integers held exactly in float registers; the key needs nbricks < 2^23.
 // Returns false if the particle has to take the float64 path.
@@ -91,7 +91,7 @@ template <int S>
 __device__ __forceinline__ bool brick_keys_f32(const float *x, const DepositGeom &G, const BrickGrid &B,
                                                unsigned int &key, float (&l)[3]) {
     const float M = 12582912.f;                      // 1.5 * 2^23: (v + M) - M = rint(v) for |v| < 2^22
-    const float Nf = (float)G.N;
+    const float Nf = (float)G.N, invN = 1.f / Nf, hN = 0.5f * invN - 0.5f;
     const float shift = G.t32 - (S == 2 ? 0.f : 0.5f);
     const float tt = G.t32 - 0.5f;                   // anchor = rint(g + tt): floor(g + shift + 0.5) TSC, floor(g + shift) CIC
     bool far = false, owned = true;
@@ -103,10 +103,11 @@ __device__ __forceinline__ bool brick_keys_f32(const float *x, const DepositGeom
         e = fmaf(x[d], G.s1, e);
         e = fmaf(x[d], G.s2, e);
         const float r = __fsub_rn(__fadd_rn(__fadd_rn(p, tt), M), M);
-        float a = r;                                 // home cell, within one box length of the box
-        a = a >= Nf ? a - Nf : a;
-        a = a < 0.f ? a + Nf : a;
-        far |= !(a >= 0.f && a < Nf);
+        // periodic wrap for positions any number of box lengths outside the box (folded boxes: x -> 2^f x mod L):
+        // a -= N * floor((a + 0.5) / N), the floor again as rint(. - 0.5) (never within 0.5 / N of a tie; the
+        // float error of the quotient stays below that for |a| < 2^20)
+        far |= !(fabsf(p) < 1048576.f);
+        float a = fmaf(-Nf, __fsub_rn(__fadd_rn(fmaf(r, invN, hN), M), M), r);
         if (d == 0 && G.slab) {
             const float h = floorf(p);               // ownership: floor of the UNSHIFTED coordinate
             const int hu = (int)(h + floorf(__fadd_rn(__fsub_rn(p, h), e)));

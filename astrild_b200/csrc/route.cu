@@ -114,7 +114,10 @@ __global__ void __launch_bounds__(256)
 route_group_kernel(const PT *__restrict__ stage_pos, const MT *__restrict__ stage_mass, const unsigned long long *__restrict__ total,
                    long long capacity, RouteGeom R, unsigned long long *__restrict__ cursor, PT *__restrict__ out_pos,
                    MT *__restrict__ out_mass) {
-    const long long n = min((long long)*total, capacity);
+    // more leavers than the staging buffer holds: the caller repeats the pass with a larger one (it reads the counts);
+    // grouping the staged part would write past out_pos, because the cursors come from the FULL counts
+    if ((long long)*total > capacity) return;
+    const long long n = (long long)*total;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long n_pad = (n + 31) & ~31LL;                        // warp-uniform trip count
     const int lane = threadIdx.x & 31;

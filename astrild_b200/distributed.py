@@ -62,7 +62,9 @@ class CudaSlabBackend:
             m = eng._to_device(mass).to(dt).contiguous()
         code = _lib.APK_F32 if dt == torch.float32 else _lib.APK_F64
         if capacity is None:
-            capacity = min(max(npart, 1), max(1 << 16, npart // 8))
+            # what left last time (+ 25 %) if that is known: unrouted input overflows npart / 8 every time, and an
+            # overflow costs a second pass after a device synchronise
+            capacity = min(max(npart, 1), max(1 << 16, npart // 8, int(1.25 * getattr(self, "_last_leavers", 0))))
         # the leavers are staged in the plan workspace: capacity * (3 + [mass]) * itemsize + 64 bytes; the workspace holds
         # at least 12 bytes per particle it is sized for
         item = 4 if dt == torch.float32 else 8
@@ -83,6 +85,7 @@ class CudaSlabBackend:
         than 1/8 of the particles change slab: rare) means a second, larger pass after a device synchronise."""
         counts = h["counts"][: self.nranks].cpu().tolist()
         total = int(sum(counts))
+        self._last_leavers = total
         if total > h["capacity"]:
             torch.cuda.synchronize(self.device)       # nothing else may be using the plan workspace
             return self.route_end(self.route_begin(h["pos"], h["mass"], h["pos_scale"], capacity=total))

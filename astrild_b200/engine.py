@@ -88,6 +88,7 @@ class PkEngine:
             self.lib.apk_plan_destroy(self._plan)
             self._plan = ct.c_void_p()
             self._workspace = None
+            self._staging = None
 
     def __del__(self):  # pragma: no cover
         try:
@@ -244,19 +245,21 @@ class PkEngine:
                 self.deposit(pos, mass, resampler, sh, pos_scale, method, out=mesh, zero=zero)
 
     def deposit_many(self, pos, mass=None, resampler: str = "tsc", shifts=(0.0,), pos_scale: float | None = None,
-                     method: str = "auto", chunk_rows: int = 1 << 25) -> list:
+                     method: str = "auto", chunk_rows: int = 1 << 25, out: list | None = None) -> list:
         """One mesh per entry of ``shifts`` (interlacing: (0, 0.5)) from the same particles.
 
         Device inputs: plain deposits.  HOST inputs (NumPy / CPU tensors): the particles are uploaded
         ONCE, in chunks, on a copy stream, and each chunk is deposited into every mesh while the next
         chunk is in flight -- the end-to-end rate is then the PCIe rate, not PCIe + compute.
         Pinned host memory gives asynchronous copies; pageable memory works but copies synchronously.
+        out: meshes to (zero and) fill instead of new ones.  Nothing here waits for the device: a caller that queues
+        several sets back to back (catalog.PkBatch) has set i + 1's first chunks in flight under set i's transforms.
         """
         cols = pos if (isinstance(pos, (tuple, list)) and len(pos) == 3 and not np.isscalar(pos[0])) else None
         first = cols[0] if cols is not None else pos
         on_host = not (isinstance(first, torch.Tensor) and first.is_cuda)
         npart = int(first.shape[0])
-        meshes = [self.new_mesh(ghosts=self.n0 < self.N) for _ in shifts]
+        meshes = list(out) if out is not None else [self.new_mesh(ghosts=self.n0 < self.N) for _ in shifts]
         if not on_host or npart <= chunk_rows:
             dev = self._positions(pos)           # one upload shared by all shifts
             dpos = (dev[0], dev[1], dev[2]) if dev[3] == _lib.APK_SOA else dev[0]
@@ -274,17 +277,24 @@ class PkEngine:
         scalar = float(mass) if (mass is not None and np.isscalar(mass)) else 1.0
         srcs = hcols + ([hmass] if hmass is not None else [])
         cur = torch.cuda.current_stream(self.device)
-        copy_stream = torch.cuda.Stream(self.device)
-        bufs = [[torch.empty((chunk_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in srcs]
-                for _ in range(2)]
-        # the allocator may hand out blocks whose last use is still queued on `cur`: order the first copy after it,
-        # and tell the allocator that the copy stream uses these blocks
-        copy_stream.wait_stream(cur)
-        for pair in bufs:
-            for buf in pair:
-                buf.record_stream(copy_stream)
-        ready = [torch.cuda.Event() for _ in range(2)]
-        free = [None, None]
+        # Staging buffers, their "free again" events and the copy stream live as long as the engine: a later call (the
+        # next snapshot of a batch) starts copying as soon as a buffer's last deposit is done, not when everything
+        # queued on `cur` -- the previous snapshot's transforms and binning -- has finished.
+        sig = (chunk_rows, tuple((t.dtype, tuple(t.shape[1:])) for t in srcs))
+        st = getattr(self, "_staging", None)
+        if st is None or st["sig"] != sig:
+            copy_stream = torch.cuda.Stream(self.device)
+            bufs = [[torch.empty((chunk_rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device) for t in srcs]
+                    for _ in range(2)]
+            # the allocator may hand out blocks whose last use is still queued on `cur`: order the first copy after
+            # it, and tell the allocator that the copy stream uses these blocks
+            copy_stream.wait_stream(cur)
+            for pair in bufs:
+                for buf in pair:
+                    buf.record_stream(copy_stream)
+            st = self._staging = {"sig": sig, "stream": copy_stream, "bufs": bufs, "free": [None, None],
+                                  "ready": [torch.cuda.Event() for _ in range(2)]}
+        copy_stream, bufs, ready, free = st["stream"], st["bufs"], st["ready"], st["free"]
         self.ensure_workspace(chunk_rows, hmass is not None, len(shifts) == 2)
         for c, a in enumerate(range(0, npart, chunk_rows)):
             b = min(a + chunk_rows, npart)
@@ -328,11 +338,12 @@ class PkEngine:
         _lib.call("apk_load_mesh", self._plan, _ptr(t), dt, mean, _ptr(out), self.stream)
         return out
 
-    def mesh_sum(self, mesh: torch.Tensor) -> float:
-        """float64 sum over the real cells of a mesh (sum of deposited mass)."""
+    def mesh_sum(self, mesh: torch.Tensor, out: torch.Tensor | None = None):
+        """float64 sum over the real cells of a mesh (sum of deposited mass).  out: a float64 device tensor whose first
+        element receives the sum WITHOUT a host synchronisation (returned as is); default: the Python float."""
         view = mesh[self.ghost_lo:self.ghost_lo + self.n0] if mesh.shape[0] != self.n0 else mesh
-        _lib.call("apk_padded_mesh_sum", self._plan, _ptr(view), _ptr(self._scratch), self.stream)
-        return float(self._scratch[0].item())
+        _lib.call("apk_padded_mesh_sum", self._plan, _ptr(view), _ptr(self._scratch if out is None else out), self.stream)
+        return float(self._scratch[0].item()) if out is None else out
 
     def store_mesh(self, mesh: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         """mesh -> contiguous float64 [n0][N][N] * scale (what paint(...).value holds)."""

@@ -139,11 +139,24 @@ class CatalogMesh:
     """
 
     def __init__(self, position, BoxSize, Nmesh, weight=None, resampler="cic", interlaced=False,
-                 compensated=False, normalize=True, pos_scale=None, device=None, method="auto"):
-        self.attrs = {"BoxSize": np.array([_box3(BoxSize)] * 3), "Nmesh": np.array([_nmesh(Nmesh)] * 3),
-                      "resampler": resampler, "interlaced": bool(interlaced), "compensated": bool(compensated)}
-        self._eng = _engine.get_engine(_nmesh(Nmesh), _box3(BoxSize), device)
+                 compensated=False, normalize=True, pos_scale=None, device=None, method="auto", fold: int = 0):
+        """fold = f > 0: the box is folded f times onto itself, x -> (2^f x) mod L (POWMES'
+        ``nfoldpow``, /root/reference/configs/powmes.config:8-10, read back at power_spectra/powmes.py:40-61): the mesh
+        then covers a box of L / 2^f, the spectrum is sampled at multiples of 2^f k_f up to 2^f times the mesh's
+        Nyquist frequency, and its amplitude and shot noise refer to the full volume L^3.  The deposit kernels wrap
+        positions any number of (folded) box lengths outside the box, so folding costs nothing extra."""
+        self._fold = int(fold)
+        if self._fold < 0 or self._fold > 10:
+            raise AstrildPkError("fold must be between 0 and 10")
+        L = _box3(BoxSize)
+        self.attrs = {"BoxSize": np.array([L] * 3), "Nmesh": np.array([_nmesh(Nmesh)] * 3),
+                      "resampler": resampler, "interlaced": bool(interlaced), "compensated": bool(compensated),
+                      "fold": self._fold}
+        self._eng = _engine.get_engine(_nmesh(Nmesh), L / 2 ** self._fold, device)
         self._pos, self._w = position, weight
+        # grid coordinate g = pos * pos_scale * N in units of the FOLDED box; an explicit pos_scale is the caller's
+        # factor to the full box's [0, 1)
+        pos_scale = None if (pos_scale is None and self._fold == 0) else (1.0 / L if pos_scale is None else pos_scale) * 2 ** self._fold
         self._normalize, self._pos_scale, self._method = bool(normalize), pos_scale, method
         if compensated and str(resampler).lower() not in ("cic", "tsc"):
             raise AstrildPkError("compensated=True needs resampler 'cic' or 'tsc'")
@@ -191,7 +204,8 @@ class CatalogMesh:
         if self._normalize:
             scale = eng.N ** 3 / total                # 1 + delta = mesh / mean: the unit cancels
         else:
-            scale = unit / (eng.L / eng.N) ** 3
+            scale = unit / (eng.L / eng.N) ** 3 / 8.0 ** self._fold     # rho of the FULL box: 2^3f folded copies overlap
+        scale *= 2.0 ** (1.5 * self._fold)            # P refers to the full volume: V = 8^f V_folded (FFTPower uses eng.L^3)
         # nbodykit CatalogMesh attrs: shotnoise = V * sum(w^2) / sum(w)^2  (= V / N unweighted)
         self.shotnoise = self._shotnoise()
         c = eng.r2c(mesh)

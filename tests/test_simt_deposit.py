@@ -138,6 +138,7 @@ def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, pair, N):
     pos[:20000] = rng.integers(0, 2 * N, (20000, 3)) * (0.5 / N) + rng.normal(0, 1e-5, (20000, 3))   # around cell faces
     pos[20000:22000] = rng.random((2000, 3)) * 3 - 1                                               # outside the box
     pos[22000:22100] = rng.integers(0, 2 * N + 1, (100, 3)) * (0.5 / N)                            # exactly on faces
+    pos[22100:26000] = rng.random((3900, 3)) * 16 - 8                                              # folded boxes: many box lengths out
     pos = pos.astype(np.float32)
     simt.simt_brick_keys.restype = None
     simt.simt_brick_keys.argtypes = [ct.c_void_p, ct.c_longlong, ct.c_int, ct.c_double, ct.c_int, ct.c_int] + [ct.c_void_p] * 3
@@ -158,12 +159,12 @@ def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, pair, N):
     want_l = cell - brick * edge + (g - home)                    # TSC: home + [-0.5, 0.5);  CIC: home + [0, 1)
     clear = np.abs(g + round_up - np.round(g + round_up)).min(axis=1) > 1e-3   # not within rounding of a face of the home cell
     np.testing.assert_array_equal(key[clear], want_key[clear])
-    np.testing.assert_allclose(l[clear], want_l[clear], rtol=0, atol=3e-4)      # float32 positions at |g| ~ 2000
+    np.testing.assert_allclose(l[clear], want_l[clear], rtol=0, atol=3e-3)      # float32 positions at |g| up to 16000
     # every particle, faces included: brick origin + payload is the particle's grid coordinate (mod N)
     kb = np.stack([key // (grid[1] * grid[2]), (key // grid[2]) % grid[1], key % grid[2]], axis=1).astype(np.int64)
     back = kb * edge + l.astype(np.float64)
     diff = (back - g + N / 2) % N - N / 2
-    assert np.abs(diff).max() < 3e-4
+    assert np.abs(diff).max() < 3e-3
     lo, hi = (-0.5, edge - 0.5) if resampler == "tsc" else (0.0, edge)
     assert (l >= lo - 3e-4).all() and (l <= hi + 3e-4).all()
     assert (kb < grid[:3]).all()

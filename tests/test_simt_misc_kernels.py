@@ -74,6 +74,27 @@ def test_route_extracts_exactly_the_leavers(misc):
         start += n
 
 
+def test_route_with_too_small_a_staging_buffer_writes_nothing(misc):
+    """More leavers than `capacity`: the counts are complete (the caller reads them and repeats the pass with a larger
+    buffer) and the grouping pass must not touch out_pos at all -- its cursors come from the FULL counts, so grouping the
+    staged part wrote past the end of out_pos with three or more ranks (found on 4 and 8 GPUs in round 2: the second
+    P(k) on the same plan came out wrong)."""
+    rng = np.random.default_rng(24)
+    N, P, rank, L = 32, 4, 1, 1.0
+    n0 = N // P
+    x, y, z = (rng.random(20000).astype(np.float32) for _ in range(3))
+    cell = np.floor(x.astype(np.float64) * N).astype(int) % N
+    want_counts = np.bincount((cell // n0)[(cell // n0) != rank], minlength=P)
+    cap = 1000                                     # << 15000 leavers
+    counts = np.zeros(2 * P, np.uint64)
+    guard = np.full((cap + 20000, 3), np.nan, np.float32)     # out_pos is the first `cap` rows; the rest is the guard
+    assert misc.simt_route(ptr(x), ptr(y), ptr(z), None, len(x), N, 1.0 / L, P, rank * n0, ptr(counts), cap, ptr(guard),
+                           None, 2) == 0
+    np.testing.assert_array_equal(counts[:P].astype(np.int64), want_counts)
+    assert int(counts[:P].sum()) > cap
+    assert np.isnan(guard).all(), "the grouping pass wrote although the staging buffer had overflowed"
+
+
 def test_peer_store_transpose_is_the_slab_transpose(misc):
     """Every rank stores its [n0][N][nz] x-slab into all receive buffers: rank s ends up with [N][ny][nz] = the
     full grid restricted to its y range."""
