@@ -7,12 +7,13 @@ all outside the numerical path:
   * ``PowerSpectrumWarning`` (undefined name in the reference, :49,100,127) is raised as
     ``PowerSpectrum3DWarning``;
   * the snapshot-consistency assert (:109) compares with ``nansum`` so empty bins do not trip it;
-  * ``_save_results`` falls back to ``.npz`` when pandas' HDF5 backend (pytables) is absent;
+  * ``_read_data`` grids ``.h5`` samples on the device (astrild_b200.ingest.assign_grid) and ``_save_results`` writes
+    through astrild_b200.catalog (``.npz`` with the same table when pandas' HDF5 backend, pytables, is absent);
+  * the reference's unused ``_get_vector_magnitude`` is not carried over;
   * ``return_modes=True`` additionally returns Nmodes (the reference drops ``power['modes']``).
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, List, Optional, Tuple, Union
 
 import numpy as np
@@ -102,28 +103,23 @@ class PowerSpectrum3D:
                              _file_paths2: List[str]) -> dict:
         return self._spectra_over_snapshots(snap_nrs, [_file_paths1, _file_paths2], None)
 
-    def _read_data(self, file_in: str, quantity: Optional[str] = None) -> np.ndarray:
-        """ """
-        value_map = np.zeros((self.sim.npar, self.sim.npar, self.sim.npar))
+    def _read_data(self, file_in: str, quantity: Optional[str] = None):
+        """The gridded field of one snapshot file: ``.npy`` maps as they are (DTFE output, float32 on disk); ``.h5``
+        tables of AMR-cell samples (columns x, y, z in box units [0,1) and the quantity) through the device-side
+        NGP assignment ``value_map[(npar*x).astype(int), ...] = values`` (ingest.assign_grid; reference:
+        power_spectrum_3d.py:140-153).  The .h5 branch returns a float64 device tensor, which ArrayMesh takes as is."""
+        if ".npy" in file_in:
+            return np.load(file_in)
         if ".h5" in file_in:
             import pandas as pd
 
-            fields = pd.read_hdf(file_in, key="df")
-            x = (self.sim.npar * fields["x"].values).astype(int)
-            y = (self.sim.npar * fields["y"].values).astype(int)
-            z = (self.sim.npar * fields["z"].values).astype(int)
-            if isinstance(quantity, (list, tuple)):
-                quantity = quantity[0]
-            value_map[(x, y, z)] = fields[quantity].values
-        elif ".npy" in file_in:
-            value_map = np.load(file_in)
-        return value_map
+            from .ingest import assign_grid
 
-    def _get_vector_magnitude(self, value_map: np.ndarray) -> np.ndarray:
-        """ Compute vector magnitude for 3D array """
-        value_map = np.sqrt(np.sum(np.square(value_map), axis=3))
-        assert len(value_map.shape) == 3
-        return value_map
+            fields = pd.read_hdf(file_in, key="df")
+            name = quantity[0] if isinstance(quantity, (list, tuple)) else quantity
+            return assign_grid(fields["x"].values, fields["y"].values, fields["z"].values, fields[name].values,
+                               self.sim.npar, device=self.device)
+        return np.zeros((self.sim.npar,) * 3)
 
     def _power_spectrum_3d(
         self,
@@ -181,25 +177,8 @@ class PowerSpectrum3D:
         return k, Pk
 
     def _save_results(self, quantity: List[str], pk: dict) -> None:
-        """
-        Save results each power spectrum of each simulations snapshot
+        """``pk_<quantities>.h5`` in ``sim.dirs["out"]``: index = k of the first snapshot, one column ``snap_<n>`` per
+        snapshot (reference: power_spectrum_3d.py:228-249); ``.npz`` with the same table when pytables is absent."""
+        from .catalog import save_power_spectra
 
-        Args:
-            quantity:
-                Quantity of whicht the power spectrum was calculated,
-                e.g. divergence velocity, matter, Phi, ...
-            pk:
-                Simulation power spectra for different snapshots/redshifts.
-        """
-        import pandas as pd
-
-        _columns = list(pk["k"].keys())
-        df = pd.DataFrame(data=pk["P"], index=pk["k"][_columns[0]])
-        filename = self.sim.dirs["out"] + "pk_%s.h5" % (("_").join(quantity))
-        if os.path.exists(filename):
-            os.remove(filename)
-        print(f"Saving results to -> {filename}")
-        try:
-            df.to_hdf(filename, key="df", mode="w")
-        except ImportError:  # pytables absent: same table as .npz
-            np.savez(filename[:-3] + ".npz", k=df.index.values, columns=np.array(_columns), P=df.values)
+        print(f"Saving results to -> {save_power_spectra(self.sim.dirs['out'], quantity, pk)}")

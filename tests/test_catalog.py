@@ -127,3 +127,42 @@ def test_folded_box_matches_the_oracle_on_folded_positions(oracle_fast, normaliz
     np.testing.assert_allclose(r.power["power"].real, want[1] * amp, rtol=2e-4)
     W, W2 = float(mass.astype(np.float64).sum()), float((mass.astype(np.float64) ** 2).sum())
     assert r.attrs["shotnoise"] == pytest.approx(L ** 3 * W2 / W ** 2 if normalize else W2 / L ** 3, rel=1e-12)
+
+
+@pytest.mark.gpu
+def test_power_spectrum_3d_compute_over_snapshots_and_saved_table(tmp_path, oracle_fast):
+    """``PowerSpectrum3D.compute`` (power_spectrum_3d.py:33-81) over two snapshot files of gridded fields, saved as the
+    reference's ``pk_<quantities>`` table and read back; values against the oracle's ArrayMesh -> FFTPower."""
+    import astrild_b200 as ab
+    from astrild_b200 import catalog
+    N, L = 24, 150.0
+    rng = np.random.default_rng(31)
+    files = {}
+    for nr in (3, 7):
+        vm = rng.normal(2.0, 1.0, (N, N, N)).astype(np.float32)
+        path = tmp_path / f"rho_{nr:03d}.npy"
+        np.save(path, vm)
+        files[nr] = (str(path), vm)
+
+    class Sim:
+        boxsize, domain_level, npar = L, N, N
+        dir_nrs = [3, 7]
+        dirs = {"out": str(tmp_path) + "/"}
+
+        def get_file_nrs(self, dsc, where, kind):
+            return [3, 7]
+
+        def get_file_paths(self, dsc, where, kind):
+            return [files[3][0], files[7][0]]
+
+    ps = ab.PowerSpectrum3D("particles", Sim())
+    pk = ps.compute(["rho"], [{"path": "x", "root": "rho", "extension": "npy"}], save=False)
+    assert list(pk["P"]) == ["snap_3", "snap_7"]
+    for nr in (3, 7):
+        want = oracle_fast.power_from_mesh(files[nr][1].astype(np.float64), None, L)
+        np.testing.assert_allclose(pk["k"]["snap_%d" % nr], want[0], rtol=1e-12)
+        np.testing.assert_allclose(pk["P"]["snap_%d" % nr], want[1], rtol=1e-4)
+    ps.compute(["rho"], [{"path": "x", "root": "rho", "extension": "npy"}], save=True)
+    idx, cols = catalog.read_table(str(tmp_path / "pk_rho.h5"))
+    np.testing.assert_array_equal(idx, pk["k"]["snap_3"])
+    np.testing.assert_array_equal(cols["snap_7"], pk["P"]["snap_7"])
