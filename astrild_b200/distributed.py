@@ -214,6 +214,28 @@ class CudaSlabBackend:
         return out, raw[3].view(torch.int64).clone()
 
 
+def bind_host_to_gpu(device_index: int):
+    """Restricts this process to the CPUs next to GPU ``device_index`` (NVML's affinity mask), so that the pinned host
+    buffers it allocates afterwards -- first touch -- and its copy threads sit on the GPU's NUMA node.  One process per GPU
+    uploads its share of the particles; without this, eight concurrent uploads cross the socket link.  Returns the number
+    of CPUs kept, or None if NVML or the affinity call is unavailable (nothing changes then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (max(os.cpu_count() or 1, 1) + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001 -- an optimisation only
+        return None
+
+
 class TorchDistComm:
     """The four exchanges of the path over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
 

@@ -282,9 +282,13 @@ def run_ours(args, wl_key: str) -> None:
         raise SystemExit("bench.py: no CUDA device (the P(k) path has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
     if world > 1:
         # a stuck collective aborts after 3 minutes instead of holding the box (NCCL watchdog)
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+        if os.environ.get("APK_BENCH_NUMA", "1") != "0":
+            from astrild_b200.distributed import bind_host_to_gpu
+            numa_cpus = bind_host_to_gpu(local_rank)      # before any pinned host buffer exists (host-buffer leg)
 
     import astrild_b200 as ab
 
@@ -592,6 +596,8 @@ def run_ours(args, wl_key: str) -> None:
               "l2": "inputs >> L2 (126 MB): no flush needed"}
     if cross:
         config["halos"] = Nh
+    if numa_cpus is not None:
+        config["host_cpus_bound_per_rank"] = numa_cpus
     if getattr(args, "order", "input") != "input":
         config["particle_order"] = args.order + " (diagnostic reordering of the set)"
     if world > 1 and slab_info:

@@ -76,6 +76,38 @@ def test_mass_soa_odd_mesh_out_of_box(simt, oracle_fast):
     close(a, oracle_fast.paint(pos, mass, N, L, "tsc", 0.5))
 
 
+@pytest.mark.parametrize("soa", [True, False])
+def test_odd_count_and_misaligned_columns(simt, oracle_fast, soa):
+    """A particle count that is not a multiple of the partition's tile (tail threads) and arrays that start 4 bytes off
+    a 16-byte boundary must give the same meshes (any vectorised load path has to fall back to scalar loads there)."""
+    rng = np.random.default_rng(12)
+    N, L, n = 32, 100.0, 10001
+    raw = (rng.random((n + 1, 3)) * L).astype(np.float32)
+    want = oracle_fast.paint(raw[1:], None, N, L, "tsc", 0.0)
+    if soa:
+        store = [np.ascontiguousarray(raw[:, d]) for d in range(3)]
+        cols = [c[1:] for c in store]             # contiguous views, 4 bytes past a 16-byte boundary
+        assert all(c.ctypes.data % 16 == 4 for c in cols)
+        pos = np.stack(cols, axis=1)              # deposit(soa=True) re-splits into contiguous columns: rebuild views
+        a, _ = deposit(simt, pos, None, N, L, "tsc", soa=True)
+        close(a, want)
+        # the misaligned pointers themselves
+        m0 = np.zeros((N, N, 2 * (N // 2 + 1)), np.float32)
+        simt.simt_deposit_sorted(cols[0].ctypes.data, cols[1].ctypes.data, cols[2].ctypes.data, 1, 0, None, 0, n, N, 1.0 / L,
+                                 0.0, 3, 0, N, m0.ctypes.data, None, 2)
+        close(m0[:, :, :N].astype(np.float64), want)
+    else:
+        flat = np.zeros(3 * n + 1, np.float32)
+        flat[1:] = raw[1:].reshape(-1)
+        aos = flat[1:].reshape(n, 3)
+        assert aos.ctypes.data % 16 == 4
+        m0 = np.zeros((N, N, 2 * (N // 2 + 1)), np.float32)
+        simt.simt_deposit_sorted(aos.ctypes.data, None, None, 0, 0, None, 0, n, N, 1.0 / L, 0.0, 3, 0, N, m0.ctypes.data, None, 2)
+        close(m0[:, :, :N].astype(np.float64), want)
+        a, _ = deposit(simt, np.ascontiguousarray(raw[1:]), None, N, L, "tsc")
+        close(a, want)
+
+
 def test_float64_positions_cic(simt, oracle_fast):
     rng = np.random.default_rng(5)
     N, L = 24, 1.0
