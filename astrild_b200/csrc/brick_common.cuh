@@ -59,11 +59,11 @@ static inline BrickGrid make_brick_grid(const DepositGeom &G, int S, bool pair) 
 template <int S>
 __device__ __forceinline__ unsigned int brick_of(const double (&x)[3], const DepositGeom &G,
                                                  const BrickGrid &B, float (&l)[3]) {
-    if (!owned_by_slab(x[0] * G.scale, G)) return 0xffffffffu;         // slab plans: not this rank's particle
+    if (!owned_by_slab(__dmul_rn(x[0], G.scale), G)) return 0xffffffffu;         // slab plans: not this rank's particle
     int b[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        const double g = x[d] * G.scale + G.shift;
+        const double g = grid_coord(x[d], G);
         const double r = rint(S == 2 ? g - 0.5 : g);                    // anchor: mesh 0's home cell
         int hl = wrap_index((long long)r, G.N);
         if (d == 0 && G.slab) {

@@ -22,14 +22,14 @@ deposit_atomic_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, cons
         double x, y, z;
         if (SOA) { x = (double)p0[p]; y = (double)p1[p]; z = (double)p2[p]; }
         else     { x = (double)p0[3 * p]; y = (double)p0[3 * p + 1]; z = (double)p0[3 * p + 2]; }
-        if (!owned_by_slab(x * G.scale, G)) continue;   // slab plans: another rank deposits it
+        if (!owned_by_slab(__dmul_rn(x, G.scale), G)) continue;   // slab plans: another rank deposits it
         float m = 1.f;
         if (mass) m = mass_f64 ? (float)((const double *)mass)[p] : ((const float *)mass)[p];
         long long ix, iy, iz;
         float wx[S], wy[S], wz[S];
-        window_1d<S>(x * G.scale + G.shift, ix, wx);
-        window_1d<S>(y * G.scale + G.shift, iy, wy);
-        window_1d<S>(z * G.scale + G.shift, iz, wz);
+        window_1d<S>(grid_coord(x, G), ix, wx);
+        window_1d<S>(grid_coord(y, G), iy, wy);
+        window_1d<S>(grid_coord(z, G), iz, wz);
         int cy[S], cz[S];
 #pragma unroll
         for (int j = 0; j < S; ++j) { cy[j] = wrap_index(iy + j, G.N); cz[j] = wrap_index(iz + j, G.N); }

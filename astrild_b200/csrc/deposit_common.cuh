@@ -58,6 +58,13 @@ __host__ __device__ __forceinline__ int DepositGeom::local_plane(long long ix) c
     return rel < nplanes ? rel : -1;
 }
 
+// g = x * scale + shift exactly as the oracle (NumPy, float64) forms it: a rounded product, then a rounded sum.  Written
+// with the intrinsics because nvcc contracts `x * scale + shift` into ONE fused multiply-add (the Makefile's
+// -ffp-contract=off reaches only the host compiler), which rounds differently for one position in ~10^13.
+__device__ __forceinline__ double grid_coord(double x, const DepositGeom &G) {
+    return __dadd_rn(__dmul_rn(x, G.scale), G.shift);
+}
+
 // slab ownership of a particle: floor of its UNSHIFTED grid coordinate lies in [own0, own0 + nown)
 __device__ __forceinline__ bool owned_by_slab(double gx_unshifted, const DepositGeom &G) {
     if (!G.slab) return true;

@@ -200,6 +200,8 @@ template <typename T, typename U> inline T atomicAdd(T *p, U v) { const T old = 
 // ---- loads, conversions, arithmetic intrinsics -------------------------------------------------------
 template <typename T> inline T __ldcs(const T *p) { return *p; }
 template <typename T> inline T __ldg(const T *p) { return *p; }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
