@@ -57,6 +57,9 @@ SIGNATURES = {
     "apk_binning_create": [ct.POINTER(_vp), _vp, _i, _i, _i] + [_vp] * 5 + [_i] + [_vp] * 6 + [_i, _i],
     "apk_binning_destroy": [_vp],
     "apk_bin_power": [_vp] * 9 + [_vp],
+    "apk_kmu_create": [ct.POINTER(_vp), _vp, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _i, _vp] + [_vp] * 6 + [_i, _i],
+    "apk_kmu_destroy": [_vp],
+    "apk_kmu_bin": [_vp] * 11,
     "apk_assign_grid": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i64, _vp, _vp, _vp, _vp],
     "apk_gather_records": [_vp, _vp, _i64, _vp, _i, _vp],
     "apk_tables_k_axis": [_i, _d, _i, _vp],

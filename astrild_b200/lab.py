@@ -222,7 +222,7 @@ class BinnedStatistic:
         self.edges = dict(zip(dims, edges))
         self.data = data
         self.attrs = attrs
-        self.shape = (len(edges[0]) - 1,)
+        self.shape = tuple(len(e) - 1 for e in edges)
         self.variables = list(data)
 
     def __getitem__(self, key):
@@ -236,7 +236,7 @@ class BinnedStatistic:
 
 
 class FFTPower:
-    """``FFTPower(first, mode='1d', second=None, kmin=0., dk=None, kmax=None)``.
+    """``FFTPower(first, mode='1d' | '2d', second=None, Nmu=, poles=, los=, kmin=0., dk=None, kmax=None)``.
 
     Result in ``self.power`` with variables ``k`` (mean |k| of the modes in the bin, NaN if
     empty), ``power`` (complex; real part is P(k)), ``modes`` (int64) and attrs including
@@ -246,10 +246,13 @@ class FFTPower:
 
     def __init__(self, first, mode="1d", Nmesh=None, BoxSize=None, second=None, los=(0, 0, 1),
                  Nmu=None, dk=None, kmin=0.0, kmax=None, poles=None, k_dtype=np.float64):
-        if mode != "1d":
-            raise AstrildPkError("only mode='1d' is implemented (the only mode astrild uses)")
-        if poles:
-            raise AstrildPkError("multipoles are not implemented on this path")
+        if mode not in ("1d", "2d"):
+            raise AstrildPkError("mode must be '1d' or '2d'")
+        poles = [] if poles is None else [int(e) for e in poles]
+        if mode == "1d":
+            Nmu = 1                                  # nbodykit: one mu bin over [0, 1]
+        elif Nmu is None:
+            Nmu = 5
         eng = first._eng
         if second is not None and second is not first and second._eng is not eng:
             raise AstrildPkError("first and second must share Nmesh, BoxSize and device")
@@ -265,10 +268,19 @@ class FFTPower:
                 raise AstrildPkError("first and second must both be interlaced or both not")
             if comp1 != comp2:
                 raise AstrildPkError("first and second must use the same window compensation")
-        binning = eng.binning(kmin, dk, kmax, comp1, c1s is not None, k_dtype)
         scale = L ** 3 * s1 * s2 / float(N) ** 6
-        res = eng.bin_power(binning, c1, c1s, c2, c2s, scale)
-        edges = binning.edges
+        res2d = None
+        if mode == "2d" or poles:
+            # (k, mu) wedges and multipoles (row N4): nbodykit's project_to_basis with Nmu bins of |mu| in [0, 1]
+            kb = eng.kmu_binning(kmin, dk, kmax, Nmu, poles, tuple(float(x) for x in los), comp1, c1s is not None, k_dtype)
+            res2d = eng.bin_kmu(kb, c1, c1s, c2, c2s, scale)
+            edges = kb.edges
+            res = {"k": res2d["poles"]["k"], "power": res2d["poles"]["power_0"], "modes": res2d["poles"]["modes"],
+                   "Nsum": None}
+        else:
+            binning = eng.binning(kmin, dk, kmax, comp1, c1s is not None, k_dtype)
+            res = eng.bin_power(binning, c1, c1s, c2, c2s, scale)
+            edges = binning.edges
         # nbodykit FFTBase._compute_3d_power: shotnoise = first.attrs.get('shotnoise', 0) for an AUTO spectrum, 0 for a
         # cross spectrum; an ArrayMesh carries none (astrild's case: the subtraction at power_spectrum_3d.py:224 is - 0)
         auto = second is None or second is first
@@ -277,10 +289,20 @@ class FFTPower:
                       "dk": 2 * np.pi / L if dk is None else dk, "kmin": kmin, "kmax": kmax,
                       "Nmu": 1, "los": list(los), "poles": [], "volume": L ** 3,
                       "shotnoise": shot, "N1": 0, "N2": 0}
-        self.power = BinnedStatistic(["k"], [edges], {"k": res["k"], "power": res["power"],
-                                                      "modes": res["modes"]}, dict(self.attrs))
+        self.attrs["Nmu"], self.attrs["poles"] = int(Nmu), list(poles)
+        if mode == "2d":
+            self.power = BinnedStatistic(["k", "mu"], [edges, res2d["muedges"]],
+                                         {"k": res2d["k"], "mu": res2d["mu"], "power": res2d["power"],
+                                          "modes": res2d["modes"]}, dict(self.attrs))
+        else:
+            self.power = BinnedStatistic(["k"], [edges], {"k": res["k"], "power": res["power"],
+                                                          "modes": res["modes"]}, dict(self.attrs))
         self.poles = None
+        if poles:
+            data = {"k": res2d["poles"]["k"], "modes": res2d["poles"]["modes"]}
+            data.update({"power_%d" % e: res2d["poles"]["power_%d" % e] for e in poles})
+            self.poles = BinnedStatistic(["k"], [edges], data, dict(self.attrs))
         self._Nsum = res["Nsum"]
 
     def run(self):
-        return self.power, None
+        return self.power, self.poles

@@ -40,6 +40,7 @@ extern "C" {
 
 typedef struct apk_plan apk_plan;
 typedef struct apk_binning apk_binning;
+typedef struct apk_kmu apk_kmu;
 
 enum { APK_F32 = 0, APK_F64 = 1 };
 enum { APK_AOS = 0, APK_SOA = 1 };                     /* (Np,3) array or three (Np,) arrays   */
@@ -175,6 +176,27 @@ int apk_binning_destroy(apk_binning *binning);
 int apk_bin_power(apk_binning *binning, const void *c1, const void *c1s, const void *c2,
                   const void *c2s, double *ksum, double *psum_re, double *psum_im,
                   int64_t *nmodes, void *stream);
+
+/* ---- (k, mu) binning and multipoles ----------------------------------------------- */
+/* nbodykit FFTPower(mode="2d", Nmu=, poles=, los=) -> project_to_basis (astrild hints at redshift-space use:
+ * README.md:11, src/astrild/particles/hutils/tpcf.py:12-60).  Grid and optional tables as in apk_binning_create, but
+ * ka / kb / kz are the SIGNED per-axis wavenumbers (host).  mu = (k . los) / |k|, binned by
+ * numpy.digitize(|mu|, linspace(0, 1, nmu + 1)); ells[0] must be 0 (the (k, mu) spectrum is the monopole-weighted sum),
+ * further entries are the requested multipoles.                                                                       */
+int apk_kmu_create(apk_kmu **kmu, apk_plan *plan, int n_a, int n_b, int nz,
+                   const double *ka_host, const double *kb_host, const double *kz_host, const double *wz_host,
+                   const double *kedges_host, int nedges, int nmu, const int *ells_host, int nell,
+                   const double *los_host /* [3] */,
+                   const double *comp_a_host, const double *comp_b_host, const double *comp_z_host,
+                   const double *phase_a_host, const double *phase_b_host, const double *phase_z_host,
+                   int dc_a, int dc_b);
+int apk_kmu_destroy(apk_kmu *kmu);
+/* DEVICE outputs, OVERWRITTEN, laid out [nedges + 1][nmu + 2] (numpy.digitize indices: k under/overflow rows, mu column
+ * 0 unused, column nmu + 1 = |mu| == 1, which is ALSO added to column nmu as nbodykit does): xsum = sum w |k|,
+ * musum = sum w |mu|, nsum = sum w; ysum_re / ysum_im [nell][nedges + 1][nmu + 2] = sum (2 ell + 1) L_ell(mu) P with the
+ * Hermitian doubling rules of project_to_basis.                                                                       */
+int apk_kmu_bin(apk_kmu *kmu, const void *c1, const void *c1s, const void *c2, const void *c2s,
+                double *xsum, double *musum, double *ysum_re, double *ysum_im, int64_t *nsum, void *stream);
 
 /* ---- ingest ------------------------------------------------------------------- */
 /* PowerSpectrum3D._read_data's gridder (src/astrild/power_spectra/power_spectrum_3d.py:142-148):

@@ -239,6 +239,137 @@ def fftpower_1d(c1: np.ndarray, c2: np.ndarray | None, N: int, L: float,
 
 
 # --------------------------------------------------------------------------------------
+# nbodykit FFTPower(mode="2d", Nmu=, poles=, los=)  -- SURVEY.md section 8f row N4 (astrild hints at redshift-space use:
+# /root/reference/README.md:11, src/astrild/particles/hutils/tpcf.py:12-60).  Restated from nbodykit 0.3.14
+# algorithms/fftpower.py (FFTPower.run: muedges = linspace(0, 1, Nmu + 1); project_to_basis) -- recollection, unpinned.
+# --------------------------------------------------------------------------------------
+def legendre(ell: int, mu):
+    """P_ell(mu) for ell = 0..8 by Bonnet's recursion (what scipy.special.legendre(ell)(mu) evaluates)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    p0, p1 = np.ones_like(mu), mu
+    if ell == 0:
+        return p0
+    for n in range(1, ell):
+        p0, p1 = p1, ((2 * n + 1) * mu * p1 - n * p0) / (n + 1)
+    return p1
+
+
+def project_to_basis_2d(p3d: np.ndarray, N: int, L: float, kedges: np.ndarray, Nmu: int, poles=(),
+                        los=(0.0, 0.0, 1.0), k_dtype=np.float64):
+    """``project_to_basis(y3d, [kedges, muedges], poles=, los=)``.
+
+    mu = (k . los) / |k| (0 at k = 0); ``dig_mu = digitize(|mu|, linspace(0, 1, Nmu + 1))``; Hermitian weights 2 on the
+    non-singular planes; for each ell of [0] + poles: ``(2 ell + 1) L_ell(mu) y`` with, on non-singular modes, the real
+    part doubled and the imaginary part dropped for even ell and the reverse for odd ell (the conjugate mode has -mu);
+    the internal mu == 1 column is folded into the last visible one.  Returns the FULL arrays (under/overflow kept):
+    xsum, musum f8 [Nx+2][Nmu+2], ysum c16 [Nell][Nx+2][Nmu+2], Nsum i8, and the list of ells (0 first).
+    """
+    kx, ky, kz = k_tables(N, L, k_dtype)
+    muedges = np.linspace(0.0, 1.0, Nmu + 1)
+    x2edges = kedges ** 2
+    Nx = len(kedges) - 1
+    ells = sorted(set([0] + [int(e) for e in poles]))
+    shape = (Nx + 2, Nmu + 2)
+    xsum, musum = np.zeros(shape), np.zeros(shape)
+    ysum = np.zeros((len(ells),) + shape, dtype=np.complex128)
+    Nsum = np.zeros(shape, dtype=np.int64)
+    w = hermitian_weights(N)
+    nonsing = w > 1.0
+    size = shape[0] * shape[1]
+    for ix in range(N):
+        k2 = (kx[ix] ** 2 + (ky ** 2)[:, None]) + (kz ** 2)[None, :]
+        dig_x = np.digitize(k2.ravel(), x2edges)
+        knorm = np.sqrt(k2)
+        kdotl = (kx[ix] * los[0] + (ky * los[1])[:, None]) + (kz * los[2])[None, :]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mu = kdotl / knorm
+        mu[knorm == 0.0] = 0.0
+        dig_mu = np.digitize(np.abs(mu).ravel(), muedges)
+        multi = np.ravel_multi_index([dig_x, dig_mu], shape)
+        wk = np.broadcast_to(w[None, :], k2.shape)
+        xsum.flat += np.bincount(multi, weights=(knorm * wk).ravel(), minlength=size)
+        musum.flat += np.bincount(multi, weights=(np.abs(mu) * wk).ravel(), minlength=size)
+        Nsum.flat += np.bincount(multi, weights=wk.ravel(), minlength=size).astype(np.int64)
+        y = np.asarray(p3d[ix], dtype=np.complex128)
+        for i, ell in enumerate(ells):
+            wy = legendre(ell, mu) * y
+            if ell % 2:
+                wy.real[:, nonsing] = 0.0
+                wy.imag[:, nonsing] *= 2.0
+            else:
+                wy.real[:, nonsing] *= 2.0
+                wy.imag[:, nonsing] = 0.0
+            wy *= 2.0 * ell + 1.0
+            ysum[i].real.flat += np.bincount(multi, weights=wy.real.ravel(), minlength=size)
+            ysum[i].imag.flat += np.bincount(multi, weights=wy.imag.ravel(), minlength=size)
+    ysum[..., -2] += ysum[..., -1]
+    musum[:, -2] += musum[:, -1]
+    xsum[:, -2] += xsum[:, -1]
+    Nsum[:, -2] += Nsum[:, -1]
+    return xsum, musum, ysum, Nsum, ells
+
+
+def fftpower_2d(c1: np.ndarray, c2: np.ndarray | None, N: int, L: float, Nmu: int = 5, poles=(), los=(0.0, 0.0, 1.0),
+                kmin: float = 0.0, dk: float | None = None, kmax: float | None = None, k_dtype=np.float64):
+    """``FFTPower(first, mode='2d', Nmu=, poles=, los=, second=, kmin=, dk=, kmax=)`` on complex fields -> dict with
+    ``k``, ``mu``, ``power`` (complex), ``modes`` of shape (Nk, Nmu) and, if poles: ``poles`` = {"k", "modes",
+    "power_<ell>"} (1-D over k: sums over the mu bins)."""
+    if c2 is None:
+        c2 = c1
+    p3d = c1 * np.conj(c2)
+    p3d[0, 0, 0] = 0.0
+    p3d *= float(L) ** 3
+    edges = k_edges(N, L, kmin, dk, kmax)
+    xsum, musum, ysum, Nsum, ells = project_to_basis_2d(p3d, N, L, edges, Nmu, poles, los, k_dtype)
+    sl = slice(1, -1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        out = {"k": (xsum / Nsum)[sl, sl], "mu": (musum / Nsum)[sl, sl], "power": (ysum[0] / Nsum)[sl, sl],
+               "modes": Nsum[sl, sl].copy(), "edges": edges, "muedges": np.linspace(0.0, 1.0, Nmu + 1)}
+        if len(poles):
+            n1 = Nsum[sl, sl].sum(axis=-1)
+            pol = {"k": xsum[sl, sl].sum(axis=-1) / n1, "modes": n1}
+            for ell in poles:
+                pol["power_%d" % ell] = ysum[ells.index(int(ell))][sl, sl].sum(axis=-1) / n1
+            out["poles"] = pol
+    return out
+
+
+def power2d_bruteforce(delta1: np.ndarray, delta2: np.ndarray | None, L: float, kedges: np.ndarray, Nmu: int, poles=(),
+                       los=(0.0, 0.0, 1.0)):
+    """The same estimator WITHOUT the Hermitian half-space bookkeeping: every one of the N^3 modes of the full complex
+    transform enters once with weight 1 and its own mu (known-answer check of project_to_basis_2d's doubling rules).
+    Returns (power[Nk][Nmu] complex, modes, {ell: P_ell[Nk]})."""
+    N = delta1.shape[0]
+    c1 = np.fft.fftn(delta1) / N ** 3
+    c2 = c1 if delta2 is None else np.fft.fftn(delta2) / N ** 3
+    p3d = c1 * np.conj(c2) * float(L) ** 3
+    p3d[0, 0, 0] = 0.0
+    kx, _, _ = k_tables(N, L)
+    k2 = (kx[:, None, None] ** 2 + kx[None, :, None] ** 2) + kx[None, None, :] ** 2
+    kn = np.sqrt(k2)
+    kd = (kx[:, None, None] * los[0] + kx[None, :, None] * los[1]) + kx[None, None, :] * los[2]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mu = kd / kn
+    mu[kn == 0] = 0.0
+    muedges = np.linspace(0.0, 1.0, Nmu + 1)
+    dx = np.digitize(k2.ravel(), kedges ** 2)
+    dm = np.digitize(np.abs(mu).ravel(), muedges)
+    dm[dm == Nmu + 1] = Nmu
+    Nx = len(kedges) - 1
+    shape = (Nx + 2, Nmu + 2)
+    multi = np.ravel_multi_index([dx, dm], shape)
+    n = np.bincount(multi, minlength=shape[0] * shape[1]).reshape(shape)
+    def binned(v):
+        return (np.bincount(multi, weights=v.real.ravel(), minlength=n.size)
+                + 1j * np.bincount(multi, weights=v.imag.ravel(), minlength=n.size)).reshape(shape)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        p2 = (binned(p3d) / n)[1:-1, 1:-1]
+        n1 = n[1:-1, 1:-1].sum(axis=-1)
+        pol = {int(ell): binned((2 * ell + 1) * legendre(int(ell), mu) * p3d)[1:-1, 1:-1].sum(axis=-1) / n1 for ell in poles}
+    return p2, n[1:-1, 1:-1], pol
+
+
+# --------------------------------------------------------------------------------------
 # astrild-level entry points (the two drop-in boundaries)
 # --------------------------------------------------------------------------------------
 def power_from_mesh(value_map1, value_map2, L: float, workers: int = 1, k_dtype=np.float64):

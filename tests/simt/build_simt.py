@@ -129,6 +129,30 @@ def build_bin(force: bool = False) -> str:
     return _gxx("bin_host.cpp", OUT_DIR, so)
 
 
+def kmu_device_part(path: str) -> str:
+    """bin_kmu.cu without its C entry points; the two inline-PTX RED helpers become plain adds."""
+    text = open(path).read()
+    text = text[:text.index("using namespace apk;")]
+    for ptx in ('asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");',
+                'asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");'):
+        assert text.count(ptx) == 1
+        text = text.replace(ptx, "*addr += v;")
+    return text
+
+
+def build_kmu(force: bool = False) -> str:
+    """-> tests/simt/_build/libapk_simt_kmu.so (bin_kmu_kernel + kmu_fold_kernel on CPU fibers)"""
+    so = os.path.join(OUT_DIR, "libapk_simt_kmu.so")
+    srcs = [os.path.join(CSRC, f) for f in ("bin_kmu.cu", "apk_common.cuh")]
+    srcs += [os.path.join(HERE, f) for f in ("simt.h", "kmu_host.cpp", "build_simt.py")]
+    if not force and _fresh(so, srcs):
+        return so
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "bin_kmu_kernels.inc"), "w") as f:
+        f.write(kmu_device_part(srcs[0]))
+    return _gxx("kmu_host.cpp", OUT_DIR, so)
+
+
 def build_misc(force: bool = False) -> str:
     """-> tests/simt/_build/libapk_simt_misc.so (direct-atomic deposit, slab routing / transpose / ghost adds,
     gridded-field helpers on CPU fibers)"""
@@ -147,3 +171,4 @@ if __name__ == "__main__":
     print(build(force=True))
     print(build_bin(force=True))
     print(build_misc(force=True))
+    print(build_kmu(force=True))

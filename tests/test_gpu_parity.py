@@ -361,3 +361,40 @@ def test_2048_mesh_64bit_indexing(ab):
     finally:
         eng.close()
         torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("cross", [False, True])
+def test_fftpower_2d_wedges_and_multipoles(ab, oracle_fast, cross):
+    """Row N4: FFTPower(mode='2d', Nmu=, poles=, los=) through the C ABI against the oracle's project_to_basis: mode
+    counts per (k, mu) bin equal, <k>, <mu>, P(k, mu) and P_0, P_2, P_4 within the fp32-mesh tolerance."""
+    from oracle import pk_oracle as o
+    N, L = 48, 300.0
+    rng = np.random.default_rng(77)
+    pos = (rng.random((150000, 3)) * L).astype(np.float32)
+    pos2 = np.mod(pos[:60000] + rng.normal(0, 2.0, (60000, 3)).astype(np.float32), L).astype(np.float32) if cross else None
+    kw = dict(resampler="tsc", interlaced=True, compensated=True, normalize=True)
+    m1 = ab.CatalogMesh(pos, L, N, **kw)
+    m2 = ab.CatalogMesh(pos2, L, N, **kw) if cross else None
+    r = ab.FFTPower(m1, mode="2d", Nmu=5, poles=[0, 2, 4], second=m2, kmin=2 * np.pi / L, los=[0, 0, 1])
+
+    def field(p):
+        real, real2 = o.paint(p, 1.0, N, L, "tsc"), o.paint(p, 1.0, N, L, "tsc", shift=0.5)
+        s = N ** 3 / real.sum()
+        return o.compensate(o.interlace_combine(o.r2c(real) * s, o.r2c(real2) * s, N, L), "tsc", True, N)
+
+    want = o.fftpower_2d(field(pos), field(pos2) if cross else None, N, L, Nmu=5, poles=(0, 2, 4), kmin=2 * np.pi / L)
+    assert r.power["modes"].shape == (len(want["edges"]) - 1, 5)
+    np.testing.assert_array_equal(r.power["modes"], want["modes"])
+    ok = want["modes"] > 0
+    np.testing.assert_allclose(r.power["k"][ok], want["k"][ok], rtol=1e-12)
+    np.testing.assert_allclose(r.power["mu"][ok], want["mu"][ok], rtol=1e-12, atol=1e-15)
+    scale = np.abs(want["power"][ok]).max()
+    np.testing.assert_allclose(r.power["power"][ok].real, want["power"][ok].real, rtol=PK_RTOL, atol=PK_RTOL * scale)
+    np.testing.assert_array_equal(r.poles["modes"], want["poles"]["modes"])
+    for ell in (0, 2, 4):
+        np.testing.assert_allclose(r.poles["power_%d" % ell].real, want["poles"]["power_%d" % ell].real, rtol=PK_RTOL,
+                                   atol=PK_RTOL * scale)
+    # the monopole of the wedges is the 1-D spectrum
+    r1 = ab.FFTPower(m1, mode="1d", second=m2, kmin=2 * np.pi / L)
+    np.testing.assert_array_equal(r1.power["modes"], r.poles["modes"])
+    np.testing.assert_allclose(r.poles["power_0"].real, r1.power["power"].real, rtol=1e-6, atol=1e-6 * scale)

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")/../astrild_b200/csrc"
 name=$1; shift
 mkdir -p ../../build/variants /tmp/apk_var_$name
-for f in api bin_power deposit_atomic deposit_sorted ingest mesh_ops power route; do
+for f in api bin_kmu bin_power deposit_atomic deposit_sorted ingest mesh_ops power route; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-ffp-contract=off \
     -I../../include -I. --expt-relaxed-constexpr "$@" -c $f.cu -o /tmp/apk_var_$name/$f.o &
 done
