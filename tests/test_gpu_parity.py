@@ -273,7 +273,7 @@ def test_error_paths(ab):
     with pytest.raises(AstrildPkError):
         ab.ParticleMesh(Nmesh=[16] * 3, BoxSize=10.0).paint(np.zeros((5, 2)))
     with pytest.raises(AstrildPkError):
-        ab.FFTPower(ab.ArrayMesh(np.zeros((8, 8, 8)), BoxSize=10.0), mode="2d")
+        ab.FFTPower(ab.ArrayMesh(np.zeros((8, 8, 8)), BoxSize=10.0), mode="3d")
 
 
 def test_streamed_host_deposit_matches_device_deposit(ab, oracle_fast):
