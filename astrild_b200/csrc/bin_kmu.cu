@@ -10,10 +10,9 @@
 // sqrt and division are correctly rounded), and both digitizes are float guesses FIXED by float64 compares against the
 // uploaded edges -- mode counts per (k, mu) bin are bit-identical to the oracle's.
 //
-// Bound: HBM for the grid reads (8 bytes per mode and grid) -- in practice the L2 atomics: every stored mode sends
-// 3 + 2 nell fire-and-forget REDs (f64 / u64) into one of NCOPY private histograms, folded at the end.  This mode is not
-// on BASELINE.json's metric; it is built for coverage and parity, not tuned (a 1024^3 interlaced auto spectrum with three
-// poles is ~10^10 REDs).
+// Bound: HBM for the grid reads (8 bytes per mode and grid) -- in practice the L2 atomics: a thread sends 3 + 2 nell
+// fire-and-forget REDs (f64 / u64) into one of NCOPY private histograms whenever the (k, mu) bin of its walk changes;
+// a last kernel folds the copies.  This mode is not on BASELINE.json's metric: built for coverage and parity.
 #include "apk_common.cuh"
 #include <cmath>
 
@@ -71,90 +70,125 @@ __device__ __forceinline__ double kmu_legendre(int ell, double mu) {
     return p1;
 }
 
-// one thread per stored mode: a warp takes 32 consecutive iz of one (ia, ib) row (256 contiguous bytes per grid)
+// One thread per stored mode; a warp takes 32 consecutive iz (256 contiguous bytes per grid and row) of one a-row and
+// walks a segment of b.  Along the walk |k| and mu move slowly, so a thread keeps the sums of its CURRENT (k, mu) bin in
+// registers and sends them (3 + 2 nell REDs) only when the bin changes.  Modes outside [kedges[0], kedges[-1]) are
+// neither read nor accumulated (nbodykit slices those rows away; for kmax = Nyquist they are ~48 % of the grid and would
+// all hit the same few addresses).
+constexpr int KMU_MAXL = 8, KMU_SEG = 32;
+
 template <bool INTERLACED, bool CROSS, bool COMP>
 __global__ void __launch_bounds__(KMU_THREADS)
 bin_kmu_kernel(KmuArgs A) {
     const int lane = threadIdx.x & 31;
     const long long warps_total = (long long)gridDim.x * (KMU_THREADS / 32);
     const long long warp_id = (long long)blockIdx.x * (KMU_THREADS / 32) + (threadIdx.x >> 5);
-    const int n_zc = (A.nz + 31) / 32;
-    const long long n_items = (long long)A.n_a * A.n_b * n_zc;
+    const int n_zc = (A.nz + 31) / 32, n_sb = (A.n_b + KMU_SEG - 1) / KMU_SEG;
+    const long long n_items = (long long)A.n_a * n_sb * n_zc;
     double *copy = A.copies + (size_t)(blockIdx.x % KMU_NCOPY) * (3 + 2 * A.nell) * A.nbins;
     double *g_x = copy, *g_mu = copy + A.nbins;
     unsigned long long *g_n = reinterpret_cast<unsigned long long *>(copy + 2 * A.nbins);
     double *g_re = copy + 3 * A.nbins, *g_im = g_re + (size_t)A.nell * A.nbins;
-    const int nedges = A.nedges, nmu = A.nmu;
+    const int nedges = A.nedges, nmu = A.nmu, nell = A.nell;
     const double e2_first = A.edges2[0], e2_last = A.edges2[nedges - 1];
 
     for (long long item = warp_id; item < n_items; item += warps_total) {
         const int zc = (int)(item % n_zc);
         const long long r = item / n_zc;
-        const int ib = (int)(r % A.n_b), ia = (int)(r / A.n_b);
+        const int sb = (int)(r % n_sb), ia = (int)(r / n_sb);
         const int iz = zc * 32 + lane;
         if (iz >= A.nz) continue;
-        const double ka = A.ka[ia], kb = A.kb[ib], kz = A.kz[iz];
-        const double k2 = __dadd_rn(__dadd_rn(__dmul_rn(ka, ka), __dmul_rn(kb, kb)), __dmul_rn(kz, kz));
-        // ---- k bin: numpy.digitize(k2, kedges^2) ----
-        int kbin;
-        if (k2 >= e2_last) kbin = nedges;
-        else if (k2 < e2_first) kbin = 0;
-        else {
-            kbin = (int)(((float)sqrt(k2) - A.kmin_f) * A.inv_dk_f) + 1;
+        const double ka = A.ka[ia], kz = A.kz[iz];
+        const double ka2 = __dmul_rn(ka, ka), kz2 = __dmul_rn(kz, kz);
+        const double kal = __dmul_rn(ka, A.los[0]), kzl = __dmul_rn(kz, A.los[2]);
+        const bool nonsingular = A.wz[iz] > 1.5f;
+        const double w = nonsingular ? 2.0 : 1.0;
+        float2 phaz = make_float2(1.f, 0.f);
+        float icaz = 1.f;
+        if (INTERLACED) phaz = kmu_cmul(A.ph_a[ia], A.ph_z[iz]);
+        if (COMP) icaz = A.ic_a[ia] * A.ic_z[iz];
+        // sums of the current bin
+        long long cur = -1;
+        double ax = 0.0, am = 0.0, are[KMU_MAXL], aim[KMU_MAXL];
+        unsigned int an = 0;
+#pragma unroll
+        for (int i = 0; i < KMU_MAXL; ++i) { are[i] = 0.0; aim[i] = 0.0; }
+        auto flush = [&]() {
+            if (cur < 0) return;
+            kmu_red_f64(g_x + cur, ax);
+            kmu_red_f64(g_mu + cur, am);
+            kmu_red_u64(g_n + cur, (unsigned long long)an);
+#pragma unroll
+            for (int i = 0; i < KMU_MAXL; ++i)
+                if (i < nell) {
+                    if (are[i] != 0.0) kmu_red_f64(g_re + (size_t)i * A.nbins + cur, are[i]);
+                    if (aim[i] != 0.0) kmu_red_f64(g_im + (size_t)i * A.nbins + cur, aim[i]);
+                    are[i] = 0.0; aim[i] = 0.0;
+                }
+            ax = 0.0; am = 0.0; an = 0;
+        };
+        const int ib1 = min((sb + 1) * KMU_SEG, A.n_b);
+        for (int ib = sb * KMU_SEG; ib < ib1; ++ib) {
+            const double kb = A.kb[ib];
+            const double k2 = __dadd_rn(__dadd_rn(ka2, __dmul_rn(kb, kb)), kz2);
+            if (k2 >= e2_last || k2 < e2_first) continue;          // outside the edges: not part of any visible bin
+            // ---- k bin: numpy.digitize(k2, kedges^2) ----
+            const double knorm = sqrt(k2);
+            int kbin = (int)(((float)knorm - A.kmin_f) * A.inv_dk_f) + 1;
             kbin = max(1, min(kbin, nedges - 1));
             while (k2 < A.edges2[kbin - 1]) --kbin;
             while (k2 >= A.edges2[kbin]) ++kbin;
-        }
-        // ---- mu and its bin: numpy.digitize(|mu|, linspace(0, 1, Nmu + 1)) -> 1 .. Nmu + 1 ----
-        const double knorm = sqrt(k2);
-        const double kdl = __dadd_rn(__dadd_rn(__dmul_rn(ka, A.los[0]), __dmul_rn(kb, A.los[1])), __dmul_rn(kz, A.los[2]));
-        const double mu = knorm > 0.0 ? kdl / knorm : 0.0;
-        const double amu = fabs(mu);
-        int mbin = min(max((int)(amu * nmu) + 1, 1), nmu + 1);
-        while (mbin > 1 && amu < A.muedges[mbin - 1]) --mbin;
-        while (mbin <= nmu && amu >= A.muedges[mbin]) ++mbin;
-        // ---- the mode's power ----
-        const size_t idx = ((size_t)ia * A.n_b + ib) * A.nz + iz;
-        float2 a = __ldcs(A.c1 + idx);
-        float2 ph = make_float2(1.f, 0.f);
-        if (INTERLACED) {
-            ph = kmu_cmul(kmu_cmul(A.ph_a[ia], A.ph_b[ib]), A.ph_z[iz]);
-            const float2 s = kmu_cmul(__ldcs(A.c1s + idx), ph);
-            a = make_float2(0.5f * (a.x + s.x), 0.5f * (a.y + s.y));
-        }
-        float pre, pim;
-        if (CROSS) {
-            float2 b = __ldcs(A.c2 + idx);
+            // ---- mu and its bin: numpy.digitize(|mu|, linspace(0, 1, Nmu + 1)) -> 1 .. Nmu + 1 ----
+            const double kdl = __dadd_rn(__dadd_rn(kal, __dmul_rn(kb, A.los[1])), kzl);
+            const double mu = knorm > 0.0 ? kdl / knorm : 0.0;
+            const double amu = fabs(mu);
+            int mbin = min(max((int)(amu * nmu) + 1, 1), nmu + 1);
+            while (mbin > 1 && amu < A.muedges[mbin - 1]) --mbin;
+            while (mbin <= nmu && amu >= A.muedges[mbin]) ++mbin;
+            const long long bin = (long long)kbin * (nmu + 2) + mbin;
+            if (bin != cur) { flush(); cur = bin; }
+            // ---- the mode's power ----
+            const size_t idx = ((size_t)ia * A.n_b + ib) * A.nz + iz;
+            float2 a = __ldcs(A.c1 + idx);
+            float2 ph = make_float2(1.f, 0.f);
             if (INTERLACED) {
-                const float2 s = kmu_cmul(__ldcs(A.c2s + idx), ph);
-                b = make_float2(0.5f * (b.x + s.x), 0.5f * (b.y + s.y));
+                ph = kmu_cmul(phaz, A.ph_b[ib]);
+                const float2 s = kmu_cmul(__ldcs(A.c1s + idx), ph);
+                a = make_float2(0.5f * (a.x + s.x), 0.5f * (a.y + s.y));
             }
-            pre = a.x * b.x + a.y * b.y;
-            pim = a.y * b.x - a.x * b.y;
-        } else {
-            pre = a.x * a.x + a.y * a.y;
-            pim = 0.f;
-        }
-        if (COMP) { const float ic = A.ic_a[ia] * A.ic_b[ib] * A.ic_z[iz]; pre *= ic; pim *= ic; }
-        if (iz == 0 && ia == A.dc_a && ib == A.dc_b) { pre = 0.f; pim = 0.f; }
-        // ---- sums ----
-        const bool nonsingular = A.wz[iz] > 1.5f;
-        const double w = nonsingular ? 2.0 : 1.0;
-        const size_t bin = (size_t)kbin * (nmu + 2) + mbin;
-        kmu_red_f64(g_x + bin, w * knorm);
-        kmu_red_f64(g_mu + bin, w * amu);
-        kmu_red_u64(g_n + bin, nonsingular ? 2ull : 1ull);
-        for (int i = 0; i < A.nell; ++i) {
-            const int ell = A.ells[i];
-            const double f = (2.0 * ell + 1.0) * kmu_legendre(ell, mu);
-            double re = f * (double)pre, im = f * (double)pim;
-            if (nonsingular) {
-                if (ell & 1) { re = 0.0; im *= 2.0; }
-                else { re *= 2.0; im = 0.0; }
+            float pre, pim;
+            if (CROSS) {
+                float2 b = __ldcs(A.c2 + idx);
+                if (INTERLACED) {
+                    const float2 s = kmu_cmul(__ldcs(A.c2s + idx), ph);
+                    b = make_float2(0.5f * (b.x + s.x), 0.5f * (b.y + s.y));
+                }
+                pre = a.x * b.x + a.y * b.y;
+                pim = a.y * b.x - a.x * b.y;
+            } else {
+                pre = a.x * a.x + a.y * a.y;
+                pim = 0.f;
             }
-            if (re != 0.0) kmu_red_f64(g_re + (size_t)i * A.nbins + bin, re);
-            if (im != 0.0) kmu_red_f64(g_im + (size_t)i * A.nbins + bin, im);
+            if (COMP) { const float ic = icaz * A.ic_b[ib]; pre *= ic; pim *= ic; }
+            if (iz == 0 && ia == A.dc_a && ib == A.dc_b) { pre = 0.f; pim = 0.f; }
+            // ---- sums ----
+            ax += w * knorm;
+            am += w * amu;
+            an += nonsingular ? 2u : 1u;
+#pragma unroll
+            for (int i = 0; i < KMU_MAXL; ++i)
+                if (i < nell) {
+                    const int ell = A.ells[i];
+                    const double f = (2.0 * ell + 1.0) * kmu_legendre(ell, mu);
+                    double re = f * (double)pre, im = f * (double)pim;
+                    if (nonsingular) {
+                        if (ell & 1) { re = 0.0; im *= 2.0; }
+                        else { re *= 2.0; im = 0.0; }
+                    }
+                    are[i] += re; aim[i] += im;
+                }
         }
+        flush();
     }
 }
 

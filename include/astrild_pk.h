@@ -191,8 +191,9 @@ int apk_kmu_create(apk_kmu **kmu, apk_plan *plan, int n_a, int n_b, int nz,
                    const double *phase_a_host, const double *phase_b_host, const double *phase_z_host,
                    int dc_a, int dc_b);
 int apk_kmu_destroy(apk_kmu *kmu);
-/* DEVICE outputs, OVERWRITTEN, laid out [nedges + 1][nmu + 2] (numpy.digitize indices: k under/overflow rows, mu column
- * 0 unused, column nmu + 1 = |mu| == 1, which is ALSO added to column nmu as nbodykit does): xsum = sum w |k|,
+/* DEVICE outputs, OVERWRITTEN, laid out [nedges + 1][nmu + 2] (numpy.digitize indices; the k under/overflow rows 0 and
+ * nedges, which nbodykit slices away, are NOT accumulated and stay zero; mu column 0 is unused, column nmu + 1 = |mu| == 1
+ * is ALSO added to column nmu as nbodykit does): xsum = sum w |k|,
  * musum = sum w |mu|, nsum = sum w; ysum_re / ysum_im [nell][nedges + 1][nmu + 2] = sum (2 ell + 1) L_ell(mu) P with the
  * Hermitian doubling rules of project_to_basis.                                                                       */
 int apk_kmu_bin(apk_kmu *kmu, const void *c1, const void *c1s, const void *c2, const void *c2s,
