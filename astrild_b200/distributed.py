@@ -358,12 +358,21 @@ class SlabPk:
 
     # ------------------------------------------------------------------ the path
     def power(self, pos, mass=None, pos_scale: float | None = None, kmin: float = 0.0, dk=None, kmax=None,
-              normalize: bool = True, routed: bool = False) -> dict:
+              normalize: bool = True, routed: bool = False, mode: str = "1d", Nmu: int | None = None, poles=(),
+              los=(0.0, 0.0, 1.0)) -> dict:
         """(k, power, modes) of this rank's particles together with everyone else's.
 
         pos: this rank's share, (Np,3) or three columns, host or device.  routed=True promises that
         every particle already sits on the rank owning floor(g_x) (skips the all-to-all-v).
+        mode='2d' (or poles): (k, mu) wedges and multipoles as FFTPower(mode='2d', Nmu=, poles=, los=) returns them --
+        ``k``, ``mu``, ``power``, ``modes`` of shape (Nk, Nmu) and ``poles`` (CUDA backend only).
         """
+        if mode not in ("1d", "2d"):
+            raise AstrildPkError("mode must be '1d' or '2d'")
+        self._kmu = None
+        if mode == "2d" or len(poles):
+            self._kmu = (1 if mode == "1d" else (5 if Nmu is None else int(Nmu)), tuple(int(e) for e in poles),
+                         tuple(float(x) for x in los), mode)
         be, P = self.backend, self.P
         ps = 1.0 / self.L if pos_scale is None else float(pos_scale)
         marks = []
@@ -461,6 +470,33 @@ class SlabPk:
         grids, total = self._ghosts_fft_transpose(meshes, mark)
         del meshes
         return self._finish(grids, total, kmin, dk, kmax, normalize, marks, mark, scalar_mass)
+
+    def _finish_kmu(self, grids, total, kmin, dk, kmax, normalize, comp, scalar_mass: float) -> dict:
+        """(k, mu) wedges and multipoles on the transposed slab (row N4): every rank bins its y-range, the float64 sums
+        and the integer mode counts are all-reduced separately, the tail is nbodykit's project_to_basis."""
+        Nmu, poles, los, mode = self._kmu
+        eng = getattr(self.backend, "eng", None)
+        if eng is None:
+            raise AstrildPkError("the (k, mu) mode needs the CUDA backend")
+        axes = {"ia": np.arange(self.N), "ib": np.arange(self.y0, self.y0 + self.ny), "key": ("slabT", self.y0, self.ny)}
+        kb = eng.kmu_binning(kmin, dk, kmax, Nmu, poles, los, comp, self.interlaced, axes=axes)
+        raw = eng.bin_kmu_raw(kb, grids[0], grids[1] if self.interlaced else None)
+        red = torch.cat([raw.reshape(-1), total.reshape(-1)[:1].to(torch.float64)])
+        cnt = raw[2].view(torch.int64).clone()
+        if self.P > 1:
+            red = self.comm.all_reduce_sum(red)
+            cnt = self.comm.all_reduce_sum(cnt)
+        host = red.cpu().numpy()
+        W = host[-1] * scalar_mass
+        N, L = self.N, self.L
+        field_scale = (N ** 3 / W) * scalar_mass if normalize else scalar_mass / (L / N) ** 3
+        res = eng.finish_kmu(host[:-1].reshape(raw.shape), cnt.cpu().numpy().astype(np.int64), kb,
+                             L ** 3 * field_scale ** 2 / float(N) ** 6)
+        res["total_mass"] = W
+        if mode == "1d":                                  # FFTPower(mode='1d', poles=...): the 1-D spectrum plus the poles
+            res = {"k": res["poles"]["k"], "power": res["poles"]["power_0"], "modes": res["poles"]["modes"],
+                   "edges": res["edges"], "poles": res["poles"], "total_mass": W}
+        return res
 
     def _timed_transpose(self, fn, stream):
         """Runs fn() between two CUDA events on `stream` (the transposes' own time, for the NVLink roofline)."""
@@ -745,6 +781,8 @@ class SlabPk:
         be, P = self.backend, self.P
         # 7. binning on the transposed slab
         comp = (self.resampler, self.interlaced) if self.compensated else None
+        if getattr(self, "_kmu", None) is not None:
+            return self._finish_kmu(grids, total, kmin, dk, kmax, normalize, comp, scalar_mass)
         binning = be.make_binning(self.y0, self.ny, kmin, dk, kmax, comp, self.interlaced)
         raw = be.bin(binning, grids[0], grids[1] if self.interlaced else None)
         mark("bin")

@@ -420,11 +420,13 @@ class PkEngine:
 
     # ------------------------------------------------------------------ stage 3': (k, mu) binning and multipoles
     def kmu_binning(self, kmin: float = 0.0, dk: float | None = None, kmax: float | None = None, Nmu: int = 5, poles=(),
-                    los=(0.0, 0.0, 1.0), compensation: tuple | None = None, interlaced: bool = False, k_dtype=np.float64):
-        """Tables for FFTPower(mode='2d', Nmu=, poles=, los=) (row N4): -> (handle, kedges, muedges, ells)."""
+                    los=(0.0, 0.0, 1.0), compensation: tuple | None = None, interlaced: bool = False, k_dtype=np.float64,
+                    axes=None):
+        """Tables for FFTPower(mode='2d', Nmu=, poles=, los=) (row N4) -> KmuBinning.  axes: as in ``binning`` (the
+        transposed slab of the multi-GPU path: all x, this rank's y)."""
         ells = tuple(sorted(set([0] + [int(e) for e in poles])))
         key = ("kmu", float(kmin), dk, kmax, int(Nmu), ells, tuple(float(x) for x in los), compensation, bool(interlaced),
-               np.dtype(k_dtype).str)
+               np.dtype(k_dtype).str, None if axes is None else axes["key"])
         got = self._binnings.get(key)
         if got is not None:
             return got
@@ -433,16 +435,20 @@ class PkEngine:
         edges = tables.k_edges(N, L, kmin, dk, kmax)
         if len(edges) < 2:
             raise AstrildPkError("binning needs at least two k edges")
-        ka = np.ascontiguousarray(kfull)
+        ia = np.arange(N) if axes is None else axes["ia"]
+        ib = np.arange(N) if axes is None else axes["ib"]
+        ka, kb_ = np.ascontiguousarray(kfull[ia]), np.ascontiguousarray(kfull[ib])
         kz = np.ascontiguousarray(kfull[: self.Nk])
         wz = np.ascontiguousarray(tables.hermitian_weights(N))
+        dc_a = int(np.flatnonzero(ia == 0)[0]) if (ia == 0).any() else -1
+        dc_b = int(np.flatnonzero(ib == 0)[0]) if (ib == 0).any() else -1
         comp, ph = [None] * 3, [None] * 3
         if compensation is not None:
             c = tables.compensation_axis(compensation[0], bool(compensation[1]), N)
-            comp = [np.ascontiguousarray(c), np.ascontiguousarray(c), np.ascontiguousarray(c[: self.Nk])]
+            comp = [np.ascontiguousarray(c[ia]), np.ascontiguousarray(c[ib]), np.ascontiguousarray(c[: self.Nk])]
         if interlaced:
             p = tables.interlace_phase_axis(N, L)
-            ph = [np.ascontiguousarray(p), np.ascontiguousarray(p), np.ascontiguousarray(p[: self.Nk])]
+            ph = [np.ascontiguousarray(p[ia]), np.ascontiguousarray(p[ib]), np.ascontiguousarray(p[: self.Nk])]
         ea = np.asarray(ells, dtype=np.int32)
         la = np.asarray(los, dtype=np.float64)
 
@@ -450,25 +456,32 @@ class PkEngine:
             return None if a is None else a.ctypes.data_as(ct.c_void_p)
 
         handle = ct.c_void_p()
-        _lib.call("apk_kmu_create", ct.byref(handle), self._plan, N, N, self.Nk, hp(ka), hp(ka), hp(kz), hp(wz), hp(edges),
-                  len(edges), int(Nmu), hp(ea), len(ells), hp(la), hp(comp[0]), hp(comp[1]), hp(comp[2]),
-                  hp(ph[0]), hp(ph[1]), hp(ph[2]), 0, 0)
+        _lib.call("apk_kmu_create", ct.byref(handle), self._plan, len(ka), len(kb_), self.Nk, hp(ka), hp(kb_), hp(kz), hp(wz),
+                  hp(edges), len(edges), int(Nmu), hp(ea), len(ells), hp(la), hp(comp[0]), hp(comp[1]), hp(comp[2]),
+                  hp(ph[0]), hp(ph[1]), hp(ph[2]), dc_a, dc_b)
         got = KmuBinning(handle, edges, np.linspace(0.0, 1.0, int(Nmu) + 1), ells, key)
         self._binnings[key] = got
         return got
 
-    def bin_kmu(self, kb: "KmuBinning", c1, c1s=None, c2=None, c2s=None, scale: float = 1.0) -> dict:
-        """(k, mu) spectrum and multipoles with nbodykit's conventions (project_to_basis tail): ``k``, ``mu``, ``power``
-        (complex), ``modes`` of shape (Nk, Nmu) and ``poles`` = {"k", "modes", "power_<ell>"}."""
-        nk1, nm2, nell = len(kb.edges) + 1, len(kb.muedges) + 1, len(kb.ells)
-        nb = nk1 * nm2
+    def bin_kmu_raw(self, kb: "KmuBinning", c1, c1s=None, c2=None, c2s=None) -> torch.Tensor:
+        """Raw sums on the device: float64 [3 + 2 nell][(nedges + 1) (Nmu + 2)] = xsum, musum, nsum (int64 bits),
+        ysum_re[nell], ysum_im[nell]."""
+        nb = (len(kb.edges) + 1) * (len(kb.muedges) + 1)
+        nell = len(kb.ells)
         out = torch.empty((3 + 2 * nell, nb), dtype=torch.float64, device=self.device)
         _lib.call("apk_kmu_bin", kb.handle, _ptr(c1), _ptr(c1s), _ptr(c2), _ptr(c2s), _ptr(out[0]), _ptr(out[1]),
                   _ptr(out[3]), _ptr(out[3 + nell]), _ptr(out[2]), self.stream)
-        host = out.cpu().numpy()
+        return out
+
+    @staticmethod
+    def finish_kmu(host: np.ndarray, nsum: np.ndarray, kb: "KmuBinning", scale: float) -> dict:
+        """Sums -> (k, mu) spectrum and multipoles with nbodykit's conventions (project_to_basis tail): ``k``, ``mu``,
+        ``power`` (complex), ``modes`` of shape (Nk, Nmu) and ``poles`` = {"k", "modes", "power_<ell>"}.
+        host: float64 [3 + 2 nell][nb] (row 2 ignored), nsum: int64 [nb]."""
+        nk1, nm2, nell = len(kb.edges) + 1, len(kb.muedges) + 1, len(kb.ells)
         xsum, musum = host[0].reshape(nk1, nm2), host[1].reshape(nk1, nm2)
-        nsum = host[2].view(np.int64).reshape(nk1, nm2)
-        ysum = (host[3:3 + nell] + 1j * host[3 + nell:]).reshape(nell, nk1, nm2) * scale
+        nsum = nsum.reshape(nk1, nm2)
+        ysum = (host[3:3 + nell] + 1j * host[3 + nell:3 + 2 * nell]).reshape(nell, nk1, nm2) * scale
         sl = slice(1, -1)
         with np.errstate(invalid="ignore", divide="ignore"):
             res = {"k": (xsum / nsum)[sl, sl], "mu": (musum / nsum)[sl, sl], "power": (ysum[0] / nsum)[sl, sl],
@@ -479,6 +492,10 @@ class PkEngine:
                 pol["power_%d" % ell] = ysum[i][sl, sl].sum(axis=-1) / n1
             res["poles"] = pol
         return res
+
+    def bin_kmu(self, kb: "KmuBinning", c1, c1s=None, c2=None, c2s=None, scale: float = 1.0) -> dict:
+        host = self.bin_kmu_raw(kb, c1, c1s, c2, c2s).cpu().numpy()
+        return self.finish_kmu(host, host[2].view(np.int64).copy(), kb, scale)
 
     def bin_power_raw(self, binning: Binning, c1, c1s=None, c2=None, c2s=None) -> torch.Tensor:
         """Raw shell sums on the device: float64 [4][nedges+1] = ksum, psum_re, psum_im, nmodes(int64 bits)."""

@@ -65,7 +65,7 @@ class ThreadComm:
         return total
 
 
-def _run_emulated(P, N, L, pos, mass, kw):
+def _run_emulated(P, N, L, pos, mass, kw, power_kw=None):
     from astrild_b200 import distributed
     shared = ThreadComm.Shared(P)
     results, errors = [None] * P, []
@@ -80,7 +80,7 @@ def _run_emulated(P, N, L, pos, mass, kw):
             # wrote past its output when more particles left than the first staging buffer held went unnoticed once)
             for _ in range(2):
                 results[rank] = runner.power(pos[rank::P], None if mass is None else mass[rank::P], kmin=2 * np.pi / L,
-                                             normalize=kw["normalize"])
+                                             normalize=kw["normalize"], **(power_kw or {}))
         except BaseException as e:  # noqa: BLE001
             errors.append(e)
             shared.barrier.abort()
@@ -117,6 +117,30 @@ def test_slab_path_matches_oracle_and_single_gpu(oracle_fast, P, kw):
         np.testing.assert_allclose(res["k"], want[0], rtol=1e-12)
         np.testing.assert_allclose(res["power"].real, want[1], rtol=1e-4)
         np.testing.assert_allclose(res["power"].real, single.power["power"].real, rtol=2e-5)
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_slab_path_kmu_wedges_and_multipoles(P):
+    """Row N4 on the slab path: every rank bins its y-range of the transposed grid into (k, mu) wedges, sums and
+    integer mode counts are reduced -- equal to the single-GPU FFTPower(mode='2d') (mode counts bit for bit)."""
+    import astrild_b200 as ab
+    N, L, Np = 64, 400.0, 200000
+    rng = np.random.default_rng(41)
+    pos = (rng.random((Np, 3)) * L).astype(np.float32)
+    kw = dict(resampler="tsc", interlaced=True, compensated=True, normalize=True, mass=False)
+    los = (0.0, 0.6, 0.8)
+    single = ab.FFTPower(ab.CatalogMesh(pos, L, N, resampler="tsc", interlaced=True, compensated=True, normalize=True),
+                         mode="2d", Nmu=4, poles=[0, 2, 4], los=los, kmin=2 * np.pi / L)
+    for res in _run_emulated(P, N, L, pos, None, kw, dict(mode="2d", Nmu=4, poles=(0, 2, 4), los=los)):
+        np.testing.assert_array_equal(res["modes"], single.power["modes"])
+        ok = res["modes"] > 0
+        np.testing.assert_allclose(res["k"][ok], single.power["k"][ok], rtol=1e-12)
+        np.testing.assert_allclose(res["mu"][ok], single.power["mu"][ok], rtol=1e-12, atol=1e-15)
+        scale = np.abs(single.power["power"][ok]).max()
+        np.testing.assert_allclose(res["power"][ok].real, single.power["power"][ok].real, rtol=2e-5, atol=2e-5 * scale)
+        for ell in (0, 2, 4):
+            np.testing.assert_allclose(res["poles"]["power_%d" % ell].real, single.poles["power_%d" % ell].real,
+                                       rtol=2e-5, atol=2e-5 * scale)
 
 
 def test_slab_path_large_sorted_deposit(oracle_fast):
