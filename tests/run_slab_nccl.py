@@ -27,6 +27,20 @@ for kw in (dict(resampler="cic", interlaced=False, compensated=False), dict(resa
             assert np.array_equal(res["modes"], want[2]), "mode counts differ"
             np.testing.assert_allclose(res["k"], want[0], rtol=1e-12)
             np.testing.assert_allclose(res["power"].real, want[1], rtol=1e-4)
+# (k, mu) wedges and multipoles over NCCL (row N4): against the oracle's project_to_basis on the same combined field
+from oracle import pk_oracle as slow  # noqa: E402
+runner = distributed.SlabPk(N, L, device=f"cuda:{local}", resampler="tsc", interlaced=True, compensated=True)
+res = runner.power(pos[rank::world], None, kmin=2 * np.pi / L, normalize=True, mode="2d", Nmu=4, poles=(0, 2), los=(0.0, 0.0, 1.0))
+if rank == 0:
+    r0, r1 = oracle.paint(pos, None, N, L, "tsc", 0.0, threads=4), oracle.paint(pos, None, N, L, "tsc", 0.5, threads=4)
+    s = N ** 3 / r0.sum()
+    field = slow.compensate(slow.interlace_combine(slow.r2c(r0) * s, slow.r2c(r1) * s, N, L), "tsc", True, N)
+    want = slow.fftpower_2d(field, None, N, L, Nmu=4, poles=(0, 2), kmin=2 * np.pi / L)
+    assert np.array_equal(res["modes"], want["modes"]), "(k, mu) mode counts differ"
+    ok = want["modes"] > 0
+    scale = np.abs(want["power"][ok]).max()
+    np.testing.assert_allclose(res["power"][ok].real, want["power"][ok].real, rtol=1e-4, atol=1e-4 * scale)
+    np.testing.assert_allclose(res["poles"]["power_2"].real, want["poles"]["power_2"].real, rtol=1e-4, atol=1e-4 * scale)
 dist.barrier()
 if rank == 0:
     print("SLAB NCCL OK", world, "ranks")
