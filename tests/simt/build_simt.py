@@ -6,7 +6,11 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "astrild_b200", "csrc")
-OUT_DIR = os.path.join(HERE, "_build")
+# APK_SIMT_ASAN=1: the same libraries built with AddressSanitizer into _build_asan (run pytest with
+# LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): an out-of-bounds access of a kernel --
+# shared memory, particle arrays, meshes, tables -- then aborts the test instead of corrupting a neighbour silently
+ASAN = os.environ.get("APK_SIMT_ASAN", "0") not in ("", "0")
+OUT_DIR = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 SO = os.path.join(OUT_DIR, "libapk_simt.so")
 HOST_PART_MARK = "static size_t max_bricks(const apk_plan *P) {"
 DYN_SMEM_DECL = "extern __shared__ __align__(16) unsigned char smem_raw[];"
@@ -90,7 +94,7 @@ def bin_device_part(path: str) -> str:
 def _gxx(src: str, inc_dir: str, so: str, extra_flags=()) -> str:
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w", "-DAPK_SIMT",
-           *extra_flags, "-I", inc_dir, "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+           *(("-fsanitize=address", "-fno-omit-frame-pointer") if ASAN else ()), *extra_flags, "-I", inc_dir, "-I", HERE, "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
            os.path.join(HERE, src), "-o", so]
     subprocess.check_call(cmd)
     return so
