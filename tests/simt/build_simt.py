@@ -71,9 +71,9 @@ def strip_host_functions(text: str) -> str:
 
 
 def misc_device_part() -> str:
-    """Device code of deposit_atomic.cu, route.cu and mesh_ops.cu in one translation unit."""
+    """Device code of deposit_atomic.cu, route.cu, mesh_ops.cu and ingest.cu in one translation unit."""
     parts = []
-    for f in ("deposit_atomic.cu", "route.cu", "mesh_ops.cu"):
+    for f in ("deposit_atomic.cu", "route.cu", "mesh_ops.cu", "ingest.cu"):
         parts.append(f"// ---- {f} ----\n" + strip_host_functions(open(os.path.join(CSRC, f)).read()))
     return "\n".join(parts)
 
@@ -161,7 +161,7 @@ def build_misc(force: bool = False) -> str:
     """-> tests/simt/_build/libapk_simt_misc.so (direct-atomic deposit, slab routing / transpose / ghost adds,
     gridded-field helpers on CPU fibers)"""
     so = os.path.join(OUT_DIR, "libapk_simt_misc.so")
-    srcs = [os.path.join(CSRC, f) for f in ("deposit_atomic.cu", "route.cu", "mesh_ops.cu", "apk_common.cuh", "deposit_common.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("deposit_atomic.cu", "route.cu", "mesh_ops.cu", "ingest.cu", "apk_common.cuh", "deposit_common.cuh")]
     srcs += [os.path.join(HERE, f) for f in ("simt.h", "misc_host.cpp", "build_simt.py")]
     if not force and _fresh(so, srcs):
         return so

@@ -111,3 +111,29 @@ extern "C" int simt_mesh_roundtrip(const double *field, long long rows, int N, d
     simt::launch(grid_of(rows * N), 256, [&] { store_mesh_kernel(mesh, rows, N, ldz, scale, back); });
     return 0;
 }
+
+// PowerSpectrum3D._read_data's NGP assignment (ingest.cu): claim pass + write pass, as apk_assign_grid launches them
+extern "C" int simt_assign_grid(const void *x, const void *y, const void *z, int pos_f64, const void *values, int val_f64,
+                                long long n, int N, double *value_map, unsigned int *winner, unsigned long long *bad,
+                                int num_sms) {
+    const size_t cells = (size_t)N * N * N;
+    std::fill(value_map, value_map + cells, 0.0);
+    std::fill(winner, winner + cells, 0u);
+    *bad = 0;
+    if (n == 0) return 0;
+    const int g = ingest_grid(n, num_sms);
+#define CLAIM(CT) simt::launch(g, 256, [&] { assign_claim_kernel<CT>((const CT *)x, (const CT *)y, (const CT *)z, n, N, winner, bad); })
+#define WRITE(CT, VT) simt::launch(g, 256, [&] { assign_write_kernel<CT, VT>((const CT *)x, (const CT *)y, (const CT *)z, (const VT *)values, n, N, winner, value_map); })
+    if (pos_f64) { CLAIM(double); if (val_f64) WRITE(double, double); else WRITE(double, float); }
+    else { CLAIM(float); if (val_f64) WRITE(float, double); else WRITE(float, float); }
+#undef CLAIM
+#undef WRITE
+    return 0;
+}
+
+// Ecosmog.compress_snapshot's record gather (ingest.cu): one CTA per piece (byte offset, destination, count)
+extern "C" int simt_gather_records(const unsigned char *raw, const long long *pieces, long long npieces, double *out) {
+    if (npieces == 0) return 0;
+    simt::launch((int)npieces, 256, [&] { gather_records_kernel(raw, (const RecordPiece *)pieces, out); });
+    return 0;
+}

@@ -196,6 +196,7 @@ template <typename T> inline unsigned __match_any_sync(unsigned, T v) {
 
 // ---- atomics (one OS thread: plain read-modify-write) ----------------------------------------------
 template <typename T, typename U> inline T atomicAdd(T *p, U v) { const T old = *p; *p = (T)(old + (T)v); return old; }
+template <typename T, typename U> inline T atomicMax(T *p, U v) { const T old = *p; if ((T)v > old) *p = (T)v; return old; }
 
 // ---- loads, conversions, arithmetic intrinsics -------------------------------------------------------
 template <typename T> inline T __ldcs(const T *p) { return *p; }
@@ -212,6 +213,10 @@ inline int __float2int_rn(float f) { return (int)std::nearbyintf(f); }      // r
 inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+inline double __hiloint2double(int hi, int lo) {
+    const unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
+    double d; std::memcpy(&d, &b, 8); return d;
+}
 inline int __double2loint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i & 0xffffffffll); }
 inline int __double2hiint(double d) { long long i; std::memcpy(&i, &d, 8); return (int)(i >> 32); }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }

@@ -22,6 +22,8 @@ def misc():
     lib.simt_transpose_p2p.argtypes = [vp, vp, i32, i32, i32, i32, i32]
     lib.simt_accumulate.argtypes = [vp, vp, i64, i32]
     lib.simt_mesh_roundtrip.argtypes = [vp, i64, i32, vp, vp, vp, f64, vp, i32]
+    lib.simt_assign_grid.argtypes = [vp, vp, vp, i32, vp, i32, i64, i32, vp, vp, vp, i32]
+    lib.simt_gather_records.argtypes = [vp, vp, i64, vp]
     return lib
 
 
@@ -129,3 +131,50 @@ def test_ghost_add_and_gridded_field_helpers(misc):
     assert np.all(mesh[:, :, N:] == 0)                              # the r2c padding is cleared
     assert abs(s_mesh[0]) < 1e-3                                    # mean removed
     np.testing.assert_allclose(back, 2.0 * mesh[:, :, :N].astype(np.float64), rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("pos_dtype,val_dtype", [(np.float64, np.float64), (np.float32, np.float32), (np.float64, np.float32)])
+def test_assign_grid_is_numpy_fancy_index_assignment(misc, pos_dtype, val_dtype):
+    """ingest.cu's two passes == value_map[(N*x).astype(int), ...] = values: truncation toward zero, a negative index
+    wraps once, the LAST of several samples of one cell wins, out-of-range samples are counted (row N1)."""
+    from oracle import ingest_oracle as io
+    rng = np.random.default_rng(5)
+    N, n = 12, 6000                                    # 3.5 samples per cell: plenty of ties
+    x, y, z = (rng.random(n).astype(pos_dtype) for _ in range(3))
+    x[:50] = -rng.random(50).astype(pos_dtype) * 0.9   # negative coordinates: NumPy counts those indices from the end
+    vals = rng.normal(size=n).astype(val_dtype)
+    want = io.read_data_assign(N, x, y, z, vals)
+    got = np.full((N, N, N), np.nan)
+    winner = np.zeros(N ** 3, np.uint32)
+    bad = np.zeros(1, np.uint64)
+    assert misc.simt_assign_grid(ptr(x), ptr(y), ptr(z), int(pos_dtype == np.float64), ptr(vals), int(val_dtype == np.float64),
+                                 n, N, ptr(got), ptr(winner), ptr(bad), 2) == 0
+    assert bad[0] == 0
+    np.testing.assert_array_equal(got, want)
+    x[7] = 1.5                                         # index 18 on a 12-cell axis: NumPy raises, the kernel counts
+    misc.simt_assign_grid(ptr(x), ptr(y), ptr(z), int(pos_dtype == np.float64), ptr(vals), int(val_dtype == np.float64),
+                          n, N, ptr(got), ptr(winner), ptr(bad), 2)
+    assert bad[0] == 1
+
+
+def test_gather_records_picks_the_float64_blocks(misc):
+    """The record gather against the reference's unpack loop on a synthetic output_poisson image (row N1)."""
+    from astrild_b200.ingest import poisson_record_pieces
+    from oracle import ingest_oracle as io
+    rng = np.random.default_rng(6)
+    nfields, levels = 3, (6, 7)
+    blocks = {}
+    for lev in levels:
+        for ib in range(1, 2 + 3 + 1):
+            ncache = int(rng.integers(0, 30))
+            if ncache:
+                blocks[(lev, ib)] = rng.random((8, nfields, ncache))
+    img = io.write_poisson(blocks, 3, 2, min(levels), max(levels))
+    want = io.unpack_poisson(img, nfields, min(levels), max(levels))
+    pieces, counts = poisson_record_pieces(img, nfields, min(levels), max(levels))
+    raw = np.frombuffer(img, dtype=np.uint8).copy()
+    for j in range(nfields):
+        out = np.full(counts[j], np.nan)
+        pj = np.ascontiguousarray(pieces[j], dtype=np.int64)
+        assert misc.simt_gather_records(ptr(raw), ptr(pj), len(pj), ptr(out)) == 0
+        np.testing.assert_array_equal(out, np.asarray(want[j]))
