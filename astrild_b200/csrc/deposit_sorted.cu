@@ -218,21 +218,34 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 #define APK_TILE_FLUSH 4095
 #endif
 constexpr int TILE_FLUSH = APK_TILE_FLUSH;            // particles between two flushes of the tile
-constexpr int TILE_THREADS = 256;
+#ifndef APK_TILE_THREADS
+#define APK_TILE_THREADS 256
+#endif
+constexpr int TILE_THREADS = APK_TILE_THREADS;
 #ifndef APK_TILE_CTAS
 #define APK_TILE_CTAS 6
 #endif
 
-#ifndef APK_TILE_ZSTRIDE
-#define APK_TILE_ZSTRIDE 32
+// APK_TILE_ROT (TSC only): 0 = every lane walks its window in the same order; 1 = lanes whose windows start on the same
+// shared-memory bank walk the x-planes of their windows in rotated order, on a tile whose x-planes are APK_TILE_XSKEW
+// banks apart (see the kernel's comment; 24.1 -> 21.2 ms for both meshes of config 3).
+#ifndef APK_TILE_ROT
+#define APK_TILE_ROT 1
 #endif
-// The tile is [TX][TY] columns of TZ = 32 cells along z, ZS words apart.  ZS = 32: the bank of a cell is its z alone.
-// Measured at 1024^3: ZS = 33 (columns skewed over the banks) is 15 % slower on snapshot-ordered input (27.2 against
-// 23.7 ms for both meshes), and so are larger bricks (16 x 16, 24 x 12: 25.8 - 27 ms).
+#ifndef APK_TILE_XSKEW
+#define APK_TILE_XSKEW 11
+#endif
+// The tile is [TX][TY] columns of TZ = 32 cells along z, YS = 32 words apart, x-planes XS words apart.  Without rotation
+// XS = TY * 32: the bank of a cell is its z alone.  (Measured at 1024^3 without rotation: a column stride of 33 words is
+// 15 % slower on snapshot-ordered input, 27.2 against 23.7 ms for both meshes, and so are larger bricks, 16 x 16 and
+// 24 x 12: 25.8 - 27 ms.)  With rotation XS = XSKEW (mod 32): bank = (z + XSKEW * x) mod 32.
 template <int S, bool PAIR> struct Tile {
     static constexpr int OFF = (S == 3) ? 1 : 0;      // window origin = home cell - OFF
-    static constexpr int TX = BX + S - 1 + (PAIR ? 1 : 0), TY = BY + S - 1 + (PAIR ? 1 : 0), TZ = BZ, ZS = APK_TILE_ZSTRIDE;
-    static constexpr int CELLS = TX * TY * ZS;
+    static constexpr int ROT = (S == 3) ? APK_TILE_ROT : 0;   // CIC: 8 updates per particle do not pay for the vote (0.70 -> 0.95 ms at 512^3)
+    static constexpr int TX = BX + S - 1 + (PAIR ? 1 : 0), TY = BY + S - 1 + (PAIR ? 1 : 0), TZ = BZ, YS = 32;
+    static constexpr int XS = TY * YS + (ROT ? ((APK_TILE_XSKEW - TY * YS) % 32 + 32) % 32 : 0);
+    static constexpr int CELLS = (TX * XS + 3) & ~3;
+    static constexpr bool PLANE_FLUSH = (S == 3);     // how the tile goes to the mesh (see the kernel)
 };
 
 // fractional bits for a chunk of n unit-mass particles: n * wmax * 2^s < 2^32, s <= SMAX (a single weight must stay
@@ -261,21 +274,24 @@ __device__ __forceinline__ void tile_home(float l, float last, float &d, int &h)
     if (S == 2) d = fminf(fmaxf(d, 0.f), 1.f);
 }
 
-// sel: 0 = mesh 0 (or the only mesh), 1 = the interlaced twin (coordinates + 0.5, home cells one further)
-template <int S, bool MASS, bool PAIR, typename VT>
+// SEL: 0 = mesh 0 (or the only mesh), 1 = the interlaced twin (coordinates + 0.5, home cells one further); a template
+// parameter so that the clamps and the shift are immediates (as a kernel argument they were re-derived per particle)
+template <int S, bool MASS, bool PAIR, int SEL, typename VT>
 __global__ void __launch_bounds__(TILE_THREADS, APK_TILE_CTAS)
 brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
                   const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
-                  DepositGeom G, BrickGrid B, float *__restrict__ mesh, int sel) {
+                  DepositGeom G, BrickGrid B, float *__restrict__ mesh) {
+    static_assert(SEL == 0 || PAIR, "the twin exists only for the interlaced pair");
     using T = Tile<S, PAIR>;
     constexpr int ZC = BrickZ<S, PAIR>::CELLS;
     __shared__ __align__(16) unsigned int tile[T::CELLS];
-    __shared__ long long xoff[T::TX];                 // mesh offset of the tile's x-planes (-1: outside the slab)
-    __shared__ int yoff[T::TY];                       // ... and of its y-rows
     __shared__ float red_s[2 * (TILE_THREADS / 32)];
+    __shared__ long long xoff[T::PLANE_FLUSH ? 1 : T::TX];   // table flush: mesh offset of the tile's x-planes (-1: outside the slab)
+    __shared__ int yoff[T::PLANE_FLUSH ? 1 : T::TY];         // ... and of its y-rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float twin = sel > 0 ? 0.5f : 0.f;
-    const float lastx = (float)(BX - 1 + (sel > 0)), lasty = (float)(BY - 1 + (sel > 0)), lastz = (float)(ZC - 1 + (sel > 0));
+    const unsigned int lanes_below = (1u << lane) - 1u;
+    constexpr float twin = SEL > 0 ? 0.5f : 0.f;
+    constexpr float lastx = (float)(BX - 1 + (SEL > 0)), lasty = (float)(BY - 1 + (SEL > 0)), lastz = (float)(ZC - 1 + (SEL > 0));
 
     // One CTA per non-empty brick, in list order (x-major: neighbouring windows meet in L2).  CTAs retire all the
     // time, so kernels of a higher-priority stream (the slab path's FFT / transpose of the first mesh) get SMs while
@@ -290,14 +306,16 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
 
         __syncthreads();                              // (persistent grids) the previous brick's flush is complete
         for (int i = tid; i < T::CELLS / 4; i += TILE_THREADS) reinterpret_cast<uint4 *>(tile)[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < T::TX) {
-            int px = bx * BX - T::OFF + tid;
-            bool ok = true;
-            if (G.slab) ok = px >= 0 && px < G.nplanes;
-            else px = wrap_index32(px, G.N);
-            xoff[tid] = ok ? (long long)px * G.N * G.ldz : -1LL;
-        } else if (tid < T::TX + T::TY) {
-            yoff[tid - T::TX] = wrap_index32(by * BY - T::OFF + tid - T::TX, G.N) * G.ldz;
+        if constexpr (!T::PLANE_FLUSH) {
+            if (tid < T::TX) {
+                int px = bx * BX - T::OFF + tid;
+                bool ok = true;
+                if (G.slab) ok = px >= 0 && px < G.nplanes;
+                else px = wrap_index32(px, G.N);
+                xoff[tid] = ok ? (long long)px * G.N * G.ldz : -1LL;
+            } else if (tid < T::TX + T::TY) {
+                yoff[tid - T::TX] = wrap_index32(by * BY - T::OFF + tid - T::TX, G.N) * G.ldz;
+            }
         }
         __syncthreads();
 
@@ -344,10 +362,12 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
             const float KZ = MASS ? 1.f : __int_as_float((127 + frac_bits - 69) << 23);
 
             // ---- one thread per particle; the next particle's loads are in flight while this one is deposited ----
+            // (with the rotation every lane of a warp makes the same number of trips: it votes across the warp)
             unsigned int p = c0 + tid;
             VT nxt = {};
             if (p < c1) nxt = vals[p];
-            for (; p < c1; p += TILE_THREADS) {
+            for (; T::ROT ? p - lane < c1 : p < c1; p += TILE_THREADS) {
+                const bool live = T::ROT ? p < c1 : true;
                 const VT v = nxt;
                 const unsigned int q = p + TILE_THREADS;
                 if (q < c1) nxt = vals[q];
@@ -370,33 +390,91 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
                     wy[0] = (ay * hxy) * ay; wy[S / 2] = fmaf(-dy, dy, 0.75f) * KXY; wy[S - 1] = (cy * hxy) * cy;
                     wz[0] = (az * hz2) * az; wz[S / 2] = fmaf(-dz, dz, 0.75f) * kz;  wz[S - 1] = (cz * hz2) * cz;
                 }
-                unsigned int *cell = tile + (hx * T::TY + hy) * T::ZS + hz;     // window origin (home - OFF) in tile coordinates
+                const int origin = hx * T::XS + hy * T::YS + hz;                // window origin (home - OFF) in tile coordinates
+                unsigned int *plane[S];
+                if constexpr (T::ROT != 0) {
+                    // Lanes whose windows start on the same bank collide on every one of the S^3 updates.  The k-th of
+                    // them (MATCH.ANY + POPC) starts with x-plane k mod S of its window instead, XSKEW banks further per
+                    // plane: the x weights and the plane pointers are rotated once per particle by selects (no dynamic
+                    // register index), the S^3 updates keep their immediate offsets.
+                    const unsigned int same = __match_any_sync(0xffffffffu, live ? (origin & 31) : 32 + lane);
+                    const unsigned int rank = (unsigned int)__popc(same & lanes_below);                 // <= 31
+                    const int rot = S == 3 ? (int)(rank - 3u * ((rank * 11u) >> 5)) : (int)(rank % (unsigned int)S);   // rank mod 3
+                    float r[S];
 #pragma unroll
-                for (int a = 0; a < S; ++a)
+                    for (int a = 0; a < S; ++a) {
+                        float v = wx[a];
+                        int xa = a;
 #pragma unroll
-                    for (int b = 0; b < S; ++b) {
-                        const float wxy = wx[a] * wy[b];
-#pragma unroll
-                        for (int c = 0; c < S; ++c) {
-                            const unsigned int fx = MASS ? (unsigned int)__float2int_rn(wxy * wz[c])
-                                                         : __float_as_uint(__fmul_rn(wxy, wz[c]));
-                            atomicAdd(cell + (a * T::TY + b) * T::ZS + c, fx);
-                        }
+                        for (int k = 1; k < S; ++k)
+                            if (rot == k) { v = wx[(a + k) % S]; xa = (a + k) % S; }
+                        r[a] = v;
+                        plane[a] = tile + origin + xa * T::XS;
                     }
+#pragma unroll
+                    for (int a = 0; a < S; ++a) wx[a] = r[a];
+                } else {
+#pragma unroll
+                    for (int a = 0; a < S; ++a) plane[a] = tile + origin + a * T::XS;
+                }
+                if (live) {
+#pragma unroll
+                    for (int a = 0; a < S; ++a)
+#pragma unroll
+                        for (int b = 0; b < S; ++b) {
+                            const float wxy = wx[a] * wy[b];
+#pragma unroll
+                            for (int c = 0; c < S; ++c) {
+                                const unsigned int fx = MASS ? (unsigned int)__float2int_rn(wxy * wz[c])
+                                                             : __float_as_uint(__fmul_rn(wxy, wz[c]));
+                                atomicAdd(plane[a] + b * T::YS + c, fx);
+                            }
+                        }
+                }
             }
             __syncthreads();   // every particle of the chunk is in the tile
 
-            // ---- tile -> mesh: one coalesced 128-byte RED per (x,y) column, zeros skipped; the tile is cleared on the way ----
+            // ---- tile -> mesh: one coalesced 128-byte RED per (x,y) column, zeros skipped; the tile is cleared on the way.
             float *mz = mesh + wrap_index32(bz * ZC - T::OFF + lane, G.N);
             const bool more = c1 < pend;
-            for (int col = warp; col < T::TX * T::TY; col += TILE_THREADS / 32) {
-                const int u = col / T::TY, w = col - u * T::TY;
-                const unsigned int fx = tile[col * T::ZS + lane];
-                if (more) tile[col * T::ZS + lane] = 0u;
-                const long long xo = xoff[u];
-                if (fx != 0u && xo >= 0) {
-                    const float val = MASS ? (float)(int)fx * quantum : (float)fx * quantum;
-                    atomicAdd(mz + xo + yoff[w], val);
+            if constexpr (T::PLANE_FLUSH) {
+                // A warp takes whole x-planes of the tile and walks their y-rows with a running mesh pointer: one LDS --
+                // the tile's own -- and a dozen instructions per column, all offsets immediate.  (Offsets from the
+                // shared-memory tables below cost three more LDS per column on the pipe the TSC kernel runs out of:
+                // 21.2 -> 20.7 ms for both meshes of config 3.  Equal column ranges per warp with running pointers: 21.3.)
+                const int py0 = wrap_index32(by * BY - T::OFF, G.N);
+                for (int u = warp; u < T::TX; u += TILE_THREADS / 32) {
+                    int px = bx * BX - T::OFF + u;
+                    bool ok = true;
+                    if (G.slab) ok = px >= 0 && px < G.nplanes;
+                    else px = wrap_index32(px, G.N);
+                    unsigned int *t = tile + u * T::XS + lane;
+                    float *row = mz + ((long long)px * G.N + py0) * G.ldz;
+                    int py = py0;
+#pragma unroll
+                    for (int w = 0; w < T::TY; ++w) {
+                        const unsigned int fx = t[w * T::YS];
+                        if (more) t[w * T::YS] = 0u;
+                        if (fx != 0u && ok) {
+                            const float val = MASS ? (float)(int)fx * quantum : (float)fx * quantum;
+                            atomicAdd(row, val);
+                        }
+                        row += G.ldz;
+                        if (++py == G.N) { py = 0; row -= (long long)G.N * G.ldz; }
+                    }
+                }
+            } else {
+                // CIC (8 updates per particle, 13 - 14 planes for 8 warps): columns dealt to the warps one by one, offsets
+                // from the tables (0.70 ms at 512^3 against 0.74 by planes)
+                for (int col = warp; col < T::TX * T::TY; col += TILE_THREADS / 32) {
+                    const int u = col / T::TY, w = col - u * T::TY;
+                    const unsigned int fx = tile[u * T::XS + w * T::YS + lane];
+                    if (more) tile[u * T::XS + w * T::YS + lane] = 0u;
+                    const long long xo = xoff[u];
+                    if (fx != 0u && xo >= 0) {
+                        const float val = MASS ? (float)(int)fx * quantum : (float)fx * quantum;
+                        atomicAdd(mz + xo + yoff[w], val);
+                    }
                 }
             }
             __syncthreads();
@@ -460,14 +538,12 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
 
     // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
     const int ctas = B.nbricks;
-    auto kern = brick_tile_kernel<S, MASS, PAIR, VT>;
-    const size_t dyn = 0;
     P->mark(3, st);
-    kern<<<ctas, TILE_THREADS, dyn, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh, 0);
+    brick_tile_kernel<S, MASS, PAIR, 0, VT><<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh);
     APK_CUDA(cudaGetLastError());
-    if (PAIR) {
+    if constexpr (PAIR) {
         if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
-        kern<<<ctas, TILE_THREADS, dyn, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh1, 1);
+        brick_tile_kernel<S, MASS, PAIR, 1, VT><<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh1);
         APK_CUDA(cudaGetLastError());
     }
     P->mark(4, st);

@@ -120,6 +120,21 @@ def build(force: bool = False) -> str:
     return compile_kernels(device_part(srcs[0]), OUT_DIR)
 
 
+def build_rot(rot: int) -> str:
+    """The same kernels built with -DAPK_TILE_ROT=<rot> (see deposit_sorted.cu); the library's own setting gives build()."""
+    text = open(os.path.join(CSRC, "deposit_sorted.cu")).read()
+    default = int(text.split("#define APK_TILE_ROT ")[1].split()[0])
+    if rot == default:
+        return build()
+    out_dir = os.path.join(OUT_DIR, f"rot{rot}")
+    so = os.path.join(out_dir, "libapk_simt.so")
+    srcs = [os.path.join(CSRC, f) for f in ("deposit_sorted.cu", "brick_common.cuh", "apk_common.cuh", "deposit_common.cuh")]
+    srcs += [os.path.join(HERE, f) for f in ("simt.h", "deposit_host.cpp", "build_simt.py")]
+    if _fresh(so, srcs):
+        return so
+    return compile_kernels(device_part(srcs[0]), out_dir, (f"-DAPK_TILE_ROT={rot}",))
+
+
 def build_bin(force: bool = False) -> str:
     """-> tests/simt/_build/libapk_simt_bin.so (bin_power_kernel + bin_fold_kernel on CPU fibers)"""
     so = os.path.join(OUT_DIR, "libapk_simt_bin.so")

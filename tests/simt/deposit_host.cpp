@@ -55,9 +55,12 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
         brick_scatter_kernel<S, PT, SOA, MASS, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
                                                   B, cursor.data(), vals.data());
     });
-    for (int sel = 0; sel < (PAIR ? 2 : 1); ++sel)
+    simt::launch(B.nbricks, TILE_THREADS, [&] {
+        brick_tile_kernel<S, MASS, PAIR, 0, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh);
+    });
+    if constexpr (PAIR)
         simt::launch(B.nbricks, TILE_THREADS, [&] {
-            brick_tile_kernel<S, MASS, PAIR, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, sel ? mesh1 : mesh, sel);
+            brick_tile_kernel<S, MASS, PAIR, 1, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh1);
         });
 }
 

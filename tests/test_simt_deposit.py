@@ -25,10 +25,14 @@ def load(path):
     return lib
 
 
-@pytest.fixture(scope="module")
-def simt():
+# the tile kernel's build variants: 0 = the lanes walk their windows in the same order, 1 = lanes whose windows start on
+# the same shared-memory bank rotate the order of their x-planes (deposit_sorted.cu, APK_TILE_ROT)
+@pytest.fixture(scope="module", params=[0, 1], ids=["rot0", "rot1"])
+def simt(request):
     import build_simt
-    return load(build_simt.build())
+    if os.environ.get("APK_SIMT_LIB"):               # another build of the same kernels (tools: A/B variants)
+        return load(os.environ["APK_SIMT_LIB"])
+    return load(build_simt.build_rot(request.param))
 
 
 def deposit(lib, pos, mass, N, L, resampler, pair=False, shift=0.0, soa=False, x0=0, n0=None):
