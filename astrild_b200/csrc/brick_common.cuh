@@ -9,13 +9,17 @@
 
 namespace apk {
 
+// Brick edge in cells along x, y.  24 x 8 since the end of round 2 (GPU calls 30 - 31, config 3 / config 2, ms per step):
+// 12 x 6: 47.4 / 3.29, 12 x 12: 46.7 / 3.23, 16 x 12: 46.4 / 3.15, 12 x 16: 46.4 / 3.17, 24 x 8: 46.3 / 3.15, 8 x 6: 48.1 --
+// larger bricks give the partition longer runs of equal keys (scatter 6.9 -> 6.4 ms) and the tile kernel less halo per
+// home cell; the tile must stay below the 48 KB of static shared memory.
 #ifndef APK_BX
-#define APK_BX 12
+#define APK_BX 24
 #endif
 #ifndef APK_BY
-#define APK_BY 6
+#define APK_BY 8
 #endif
-constexpr int BX = APK_BX, BY = APK_BY;         // brick edge in cells along x, y
+constexpr int BX = APK_BX, BY = APK_BY;
 constexpr int BZ = 32;                          // z-lanes of a column = tile cells along z (one warp)
 // home cells of a brick along z: a column's 32 lanes are exactly its 32 tile cells -- the home cells, the S - 1 halo
 // cells of the window and, for the interlaced pair (PAIR), one more: the twin's home cell is the same cell or the

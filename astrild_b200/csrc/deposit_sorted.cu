@@ -8,7 +8,7 @@
 // traffic is real but not credited.
 //
 // Pipeline (all on one stream, no host sync):
-//   1. brick_count_kernel   every particle -> key of the brick (12 x 6 x 29..31 home cells) that holds its mesh-0 HOME
+//   1. brick_count_kernel   every particle -> key of the brick (24 x 8 x 29..31 home cells) that holds its mesh-0 HOME
 //                           cell; per-brick counts with one RED per warp-run of equal keys (snapshot order is spatially
 //                           coherent).  float32 positions: ~40 FP32 instructions per particle, no float64, no
 //                           conversions, no integer division (brick_keys_f32); float64 positions: the oracle's expression.
@@ -21,7 +21,8 @@
 //      the twin's home cell is the same cell or the next one per axis, so its tile is one cell longer per axis
 //      (bricks hold one z-cell less) and its coordinates are the payload's + 0.5.  No second copies, no flags.
 //   4. brick_tile_kernel    one CTA per non-empty brick, one THREAD per particle, the brick's window of the mesh as
-//                           fixed-point integers in shared memory, native ATOMS.ADD (see the kernel's comment).
+//                           fixed-point integers in shared memory, native ATOMS.ADD, bank-aware walking order (see
+//                           the kernel's comment).
 //      Tried and removed in round 2 (profiles/r02_measurements.md): a one-pass partition into paged buckets (21.7 ms
 //      against 7.5 + 9.4 ms for count + scatter at 1024^3, and it can dead-lock on randomly ordered input); filing the
 //      twin's boundary particles twice with sign flags (14 % more payload, ~110 more instructions per particle in
@@ -193,12 +194,25 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 // B200, tools/ubench/atoms.cu: 0.7 cycles per warp-instruction and SM when the 32 lanes hit 32 banks, 0.7 k when k lanes
 // share a bank -- the SAME address counts like any other bank conflict -- and ~1.9 for random cells; the float atomicAdd
 // is a CAS loop at 3.5 - 9.6).  No in-brick sort, no per-cell loop: all 32 lanes work on every instruction, whatever the
-// cell occupancy.  ncu (profiles/): the shared-memory pipe is what bounds this kernel (> 85 % busy with ATOMS
-// wavefronts, 3.3 per instruction); particle order inside the brick does not change that (measured: input order,
-// shuffled and cell-sorted sets within 10 %, the cell-sorted one slowest).
+// cell occupancy.  ncu (profiles/): the shared-memory pipe is what bounds this kernel (88 - 92 % busy, 85 % of its
+// wavefronts are the ATOMS'); its time follows the number of ATOMS wavefronts, i.e. the largest number of lanes on one
+// bank per instruction: 3.1 - 3.3 when every lane walks its window in the same order (input order, shuffled and
+// cell-sorted sets within 10 %, the cell-sorted one slowest).
+//   Rotation (TSC; round 2, GPU calls 24 - 29): lanes whose windows START on the same bank collide on all 27 updates.
+//   They are ranked with one MATCH.ANY + POPC per particle, and the k-th of them walks the x-planes of its window
+//   starting with plane k mod 3; the tile's x-planes are 11 banks apart (bank = z + 11 x), so those lanes now sit on
+//   different banks at every step.  2.59 wavefronts per ATOMS (from 3.3 at 512^3), 20.7 ms for both meshes of config 3
+//   (from 24.1).  Measured and not kept: the rank from five ballots instead of MATCH (same time); skews 3, 5, 9, 13
+//   (within 2 %); rotating the y-rows as well by the next digit of the rank, on a tile skewed (9 x + 3 y + z) (25.1 ms:
+//   the 9 extra selects); k-th lane -> plane min(k, 2) or k & 1 (22.3 - 23.1 ms); 7 - 8 CTAs per SM at 32 registers, 128
+//   or 512 threads per brick (+- 0.5 %); CIC, with 8 updates per particle, loses to the vote (0.70 -> 0.95 ms at 512^3)
+//   and keeps the plain order.  A CPU model of the bench set (max lanes per bank over the 27 steps, particles in the
+//   scatter's arrival order) gives 3.13 -> 2.13 for this rule and 2.06 for a greedy choice among all 27 digit-wise
+//   rotations: the family is exhausted; only a cyclic walk (lane L on bank L + t at step t) would be conflict-free, and
+//   that needs the 27 weights indexed by a per-lane offset, i.e. dynamic register indexing.
 //   Quantum: 2^-s of the largest |mass| in the chunk (1 for unit masses), s chosen PER CHUNK of <= TILE_FLUSH particles
 //   as large as 32 bits allow if every particle of the chunk put its largest possible weight (1 for CIC, 0.75^3 for
-//   TSC) into one cell: s = 22 for the ~2200 particles of a brick at one particle per cell (TSC), 20 - 21 for a full
+//   TSC) into one cell: s = 20 for the ~5600 particles of a brick at one particle per cell (TSC), 20 for a full
 //   chunk, up to 24 for sparse bricks.
 //   Unit masses: the float -> fixed conversion costs nothing.  The three axis weights carry the factors 2^-40, 2^-40 and
 //   2^(s - 69), so the product of the three is w * 2^(s - 149): a SUBNORMAL float whose bit pattern IS the integer
@@ -215,7 +229,7 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
 //   scattered STS and LDS per particle), its five barriers per chunk and the idle lanes of the shorter queues
 //   (utilisation 0.72) cost more than the conflicts.  Removed.
 #ifndef APK_TILE_FLUSH
-#define APK_TILE_FLUSH 4095
+#define APK_TILE_FLUSH 8191
 #endif
 constexpr int TILE_FLUSH = APK_TILE_FLUSH;            // particles between two flushes of the tile
 #ifndef APK_TILE_THREADS
@@ -223,7 +237,7 @@ constexpr int TILE_FLUSH = APK_TILE_FLUSH;            // particles between two f
 #endif
 constexpr int TILE_THREADS = APK_TILE_THREADS;
 #ifndef APK_TILE_CTAS
-#define APK_TILE_CTAS 6
+#define APK_TILE_CTAS 5
 #endif
 
 // APK_TILE_ROT (TSC only): 0 = every lane walks its window in the same order; 1 = lanes whose windows start on the same

@@ -101,6 +101,9 @@ extern "C" long long simt_deposit_sorted(const void *p0, const void *p1, const v
 
 // brick_keys for every particle (float32 positions, whole-mesh plan): key and brick-local coordinates, for a direct
 // check of the float-register index arithmetic at large mesh sizes.  pair: the interlaced pair's brick grid.
+// brick edge along x, y as this build has them (APK_BX, APK_BY)
+extern "C" void simt_brick_edges(int *bxy) { bxy[0] = BX; bxy[1] = BY; }
+
 extern "C" void simt_brick_keys(const float *xyz, long long np, int N, double pos_scale, int resampler, int pair,
                                 unsigned int *key, float *l, int *grid) {
     const DepositGeom G = make_geom(N, pos_scale, 0.0, resampler, 0, N, 1, 2);

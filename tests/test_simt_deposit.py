@@ -164,7 +164,7 @@ def test_twin_wrapping_inside_one_brick(simt, oracle_fast, resampler, N, f64):
 @pytest.mark.parametrize("pair", [0, 1])
 @pytest.mark.parametrize("N", [1024, 2048, 1000])
 def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, pair, N):
-    """The partition's index arithmetic stays in float32 registers (cells up to 2047, bricks up to 341, no integer
+    """The partition's index arithmetic stays in float32 registers (cells up to 2047, bricks up to 256, no integer
     division, no conversion): checked for every particle against integer arithmetic on the float64 grid coordinate.
     Away from cell faces the key is the brick of the mesh-0 home cell and the payload its coordinate in that brick;
     AT a face (within rounding) either neighbour is allowed, but key and payload must still name the same point."""
@@ -185,7 +185,10 @@ def test_brick_keys_at_benchmark_mesh_sizes(simt, resampler, pair, N):
                          l.ctypes.data, grid.ctypes.data)
     zc = 32 - ({"cic": 1, "tsc": 2}[resampler]) - pair
     assert grid[3] == zc
-    edge = np.array([12, 6, zc])
+    bxy = np.zeros(2, np.int32)
+    simt.simt_brick_edges.restype = None
+    simt.simt_brick_edges(bxy.ctypes.data_as(ct.c_void_p))
+    edge = np.array([bxy[0], bxy[1], zc])
     g = pos.astype(np.float64) * N                               # pos_scale = 1: Ramses-style coordinates
     round_up = 0.5 if resampler == "tsc" else 0.0
     home = np.floor(g + round_up).astype(np.int64)
