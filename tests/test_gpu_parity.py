@@ -45,7 +45,9 @@ def test_deposit_matches_oracle(ab, oracle_fast, method, resampler, N):
             want = oracle_fast.paint(pos, m, N, L, resampler, shift)
             assert got.shape == (N, N, N)
             scale = np.abs(want).max()
-            np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * scale)
+            # float32 mesh + the sorted path's fixed-point tile: one deposit is rounded to 2^-18 .. 2^-21 of the chunk's
+            # largest mass (2^-18 = 3.8e-6 for a full chunk of 8191 CIC particles, the case of the 32^3 mesh here)
+            np.testing.assert_allclose(got, want, rtol=0, atol=5e-6 * scale)
             assert got.sum() == pytest.approx(want.sum(), rel=1e-6)
 
 
@@ -64,7 +66,7 @@ def test_deposit_layouts_and_dtypes_agree(ab, oracle_fast, method):
     }
     for name, (p, m) in variants.items():
         got = pm.paint(p, mass=m, resampler="tsc", method=method).value
-        np.testing.assert_allclose(got, want, rtol=0, atol=2e-6 * want.max(), err_msg=name)
+        np.testing.assert_allclose(got, want, rtol=0, atol=5e-6 * want.max(), err_msg=name)
 
 
 def test_deposit_known_weights(ab):
