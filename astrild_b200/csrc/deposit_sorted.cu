@@ -17,6 +17,9 @@
 //                           atomicAdd on the brick's cursor and writes its payload = brick-local coordinates as
 //                           3 floats (+ mass), contiguously.  One read and one write of the particles replace a
 //                           multi-pass radix sort; order inside a brick is arbitrary (the deposit does not care).
+//                           (One array per coordinate instead of 12-byte records, round 2 call 34: the tile kernel's
+//                           loads become one wavefront each, 20.5 -> 20.2 ms, but the scatter writes three streams of
+//                           short runs: 6.4 -> 11.1 ms.  Records kept.)
 //      Interlaced pair (apk_deposit_interlaced): the SAME partition and the same 12-byte payload serve both meshes --
 //      the twin's home cell is the same cell or the next one per axis, so its tile is one cell longer per axis
 //      (bricks hold one z-cell less) and its coordinates are the payload's + 0.5.  No second copies, no flags.
@@ -34,43 +37,6 @@
 
 namespace apk {
 
-// The brick-ordered payload in the workspace.  APK_PAYLOAD_SOA = 1: one array per coordinate (+ mass), `stride` floats
-// apart -- the tile kernel's three loads per particle are then one wavefront each on the load/store pipe it runs out
-// of (12-byte records: 2.2 each), and the scatter's stores of a run are contiguous.  0: records of 12 / 16 bytes.
-#ifndef APK_PAYLOAD_SOA
-#define APK_PAYLOAD_SOA 0
-#endif
-template <typename VT>
-__device__ __forceinline__ void payload_store(VT *__restrict__ vals, unsigned int stride, unsigned int p, const VT &v) {
-#if APK_PAYLOAD_SOA
-    float *b = reinterpret_cast<float *>(vals);
-    b[p] = v.x; b[(size_t)stride + p] = v.y; b[2 * (size_t)stride + p] = v.z;
-    if constexpr (sizeof(VT) == 16) b[3 * (size_t)stride + p] = v.m;
-#else
-    vals[p] = v;
-#endif
-}
-template <typename VT>
-__device__ __forceinline__ VT payload_load(const VT *__restrict__ vals, unsigned int stride, unsigned int p) {
-#if APK_PAYLOAD_SOA
-    const float *b = reinterpret_cast<const float *>(vals);
-    VT v;
-    v.x = __ldg(b + p); v.y = __ldg(b + (size_t)stride + p); v.z = __ldg(b + 2 * (size_t)stride + p);
-    if constexpr (sizeof(VT) == 16) v.m = __ldg(b + 3 * (size_t)stride + p);
-    return v;
-#else
-    return vals[p];
-#endif
-}
-template <typename VT>
-__device__ __forceinline__ float payload_mass(const VT *__restrict__ vals, unsigned int stride, unsigned int p) {
-#if APK_PAYLOAD_SOA
-    return __ldg(reinterpret_cast<const float *>(vals) + 3 * (size_t)stride + p);
-#else
-    return vals[p].m;
-#endif
-}
-static inline size_t payload_stride(long long np) { return ((size_t)np + 63) & ~(size_t)63; }   // floats: arrays 256-byte aligned
 
 template <int S, typename PT, bool SOA>
 __global__ void __launch_bounds__(PART_THREADS)
@@ -178,7 +144,7 @@ template <int S, typename PT, bool SOA, bool MASS, typename VT>
 __global__ void __launch_bounds__(PART_THREADS, APK_SCATTER_MIN_CTAS)
 brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const PT *__restrict__ p2,
                      const void *__restrict__ mass, int mass_f64, long long np, DepositGeom G,
-                     BrickGrid B, unsigned int *__restrict__ cursor, VT *__restrict__ vals, unsigned int stride) {
+                     BrickGrid B, unsigned int *__restrict__ cursor, VT *__restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const long long tile = (long long)PART_THREADS * PART_ITEMS;
     const long long step = (long long)gridDim.x * tile;
@@ -218,7 +184,7 @@ brick_scatter_kernel(const PT *__restrict__ p0, const PT *__restrict__ p1, const
             }
             if (k > 0) {
                 const unsigned int ps = __shfl_sync(0xffffffffu, pslot, phead) + poffset;
-                if (plive) payload_store(vals, stride, ps, pv);
+                if (plive) vals[ps] = pv;
             }
             pv = v; pslot = slot; phead = head; poffset = offset; plive = live;
         }
@@ -329,7 +295,7 @@ __device__ __forceinline__ void tile_home(float l, float last, float &d, int &h)
 // parameter so that the clamps and the shift are immediates (as a kernel argument they were re-derived per particle)
 template <int S, bool MASS, bool PAIR, int SEL, typename VT>
 __global__ void __launch_bounds__(TILE_THREADS, APK_TILE_CTAS)
-brick_tile_kernel(const VT *__restrict__ vals, unsigned int stride, const unsigned int *__restrict__ brick_start,
+brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ brick_start,
                   const unsigned int *__restrict__ filled, const unsigned int *__restrict__ nfilled_ptr,
                   DepositGeom G, BrickGrid B, float *__restrict__ mesh) {
     static_assert(SEL == 0 || PAIR, "the twin exists only for the interlaced pair");
@@ -380,7 +346,7 @@ brick_tile_kernel(const VT *__restrict__ vals, unsigned int stride, const unsign
             if constexpr (MASS) {
                 float top = 0.f, sum = 0.f;
                 for (unsigned int p = c0 + tid; p < c1; p += TILE_THREADS) {
-                    const float a = fabsf(payload_mass(vals, stride, p));
+                    const float a = fabsf(vals[p].m);
                     top = fmaxf(top, a);
                     sum += a;
                 }
@@ -416,12 +382,12 @@ brick_tile_kernel(const VT *__restrict__ vals, unsigned int stride, const unsign
             // (with the rotation every lane of a warp makes the same number of trips: it votes across the warp)
             unsigned int p = c0 + tid;
             VT nxt = {};
-            if (p < c1) nxt = payload_load(vals, stride, p);
+            if (p < c1) nxt = vals[p];
             for (; T::ROT ? p - lane < c1 : p < c1; p += TILE_THREADS) {
                 const bool live = T::ROT ? p < c1 : true;
                 const VT v = nxt;
                 const unsigned int q = p + TILE_THREADS;
-                if (q < c1) nxt = payload_load(vals, stride, q);
+                if (q < c1) nxt = vals[q];
                 float dx, dy, dz;
                 int hx, hy, hz;
                 tile_home<S>(v.x + twin, lastx, dx, hx);
@@ -542,7 +508,7 @@ static size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t deposit_sorted_workspace_bytes(const apk_plan *P, long long np, int with_mass, int /*pair*/) {
     if (np <= 0) return 0;
     const size_t vs = with_mass ? sizeof(P4) : sizeof(P3);
-    return align256(vs * payload_stride(np)) + 4 * align256(4 * (max_bricks(P) + 2)) +
+    return align256(vs * (size_t)np) + 4 * align256(4 * (max_bricks(P) + 2)) +
            2 * align256(4 * (max_bricks(P) / SCAN_SEG + 2)) + 256;
 }
 
@@ -560,8 +526,7 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     APK_REQUIRE(np < 0xffffffffLL, "apk_deposit: more than 2^32-1 particles on one device");
     APK_REQUIRE((size_t)B.nbricks <= max_bricks(P), "apk_deposit: brick tables too small (internal)");
     unsigned char *w = (unsigned char *)P->workspace;
-    VT *vals = (VT *)w; w += align256(sizeof(VT) * payload_stride(np));
-    const unsigned int stride = (unsigned int)payload_stride(np);
+    VT *vals = (VT *)w; w += align256(sizeof(VT) * (size_t)np);
     const size_t tab = align256(4 * (max_bricks(P) + 2));
     unsigned int *counts = (unsigned int *)w; w += tab;
     unsigned int *brick_start = (unsigned int *)w; w += tab;
@@ -585,17 +550,17 @@ static int run_sorted(apk_plan *P, const void *p0, const void *p1, const void *p
     APK_CUDA(cudaGetLastError());
     P->mark(2, st);
     brick_scatter_kernel<S, PT, SOA, MASS, VT><<<pb, PART_THREADS, 0, st>>>(
-        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals, stride);
+        (const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_dtype == APK_F64, np, G, B, cursor, vals);
     APK_CUDA(cudaGetLastError());
 
     // one CTA per brick (CTAs beyond the number of non-empty bricks, which only the device knows, exit at once)
     const int ctas = B.nbricks;
     P->mark(3, st);
-    brick_tile_kernel<S, MASS, PAIR, 0, VT><<<ctas, TILE_THREADS, 0, st>>>(vals, stride, brick_start, filled, counter + 1, G, B, mesh);
+    brick_tile_kernel<S, MASS, PAIR, 0, VT><<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh);
     APK_CUDA(cudaGetLastError());
     if constexpr (PAIR) {
         if (P->first_mesh_event) APK_CUDA(cudaEventRecord(P->first_mesh_event, st));
-        brick_tile_kernel<S, MASS, PAIR, 1, VT><<<ctas, TILE_THREADS, 0, st>>>(vals, stride, brick_start, filled, counter + 1, G, B, mesh1);
+        brick_tile_kernel<S, MASS, PAIR, 1, VT><<<ctas, TILE_THREADS, 0, st>>>(vals, brick_start, filled, counter + 1, G, B, mesh1);
         APK_CUDA(cudaGetLastError());
     }
     P->mark(4, st);

@@ -34,8 +34,7 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
          const DepositGeom &G, float *mesh, float *mesh1, int num_sms) {
     using VT = typename std::conditional<MASS, P4, P3>::type;
     const BrickGrid B = make_brick_grid(G, S, PAIR);
-    std::vector<VT> vals(payload_stride(np) + 1);
-    const unsigned int stride = (unsigned int)payload_stride(np);
+    std::vector<VT> vals((size_t)np + 1);
     std::vector<unsigned int> counts(B.nbricks + 2, 0u), start(B.nbricks + 2, 0xdeadbeefu), cursor(B.nbricks + 2, 0xdeadbeefu),
         filled(B.nbricks + 2, 0xdeadbeefu);
     const int nseg = (B.nbricks + SCAN_SEG - 1) / SCAN_SEG;
@@ -54,14 +53,14 @@ void run(const void *p0, const void *p1, const void *p2, const void *mass, int m
     });
     simt::launch(pb, PART_THREADS, [&] {
         brick_scatter_kernel<S, PT, SOA, MASS, VT>((const PT *)p0, (const PT *)p1, (const PT *)p2, mass, mass_f64, np, G,
-                                                  B, cursor.data(), vals.data(), stride);
+                                                  B, cursor.data(), vals.data());
     });
     simt::launch(B.nbricks, TILE_THREADS, [&] {
-        brick_tile_kernel<S, MASS, PAIR, 0, VT>(vals.data(), stride, start.data(), filled.data(), counter + 1, G, B, mesh);
+        brick_tile_kernel<S, MASS, PAIR, 0, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh);
     });
     if constexpr (PAIR)
         simt::launch(B.nbricks, TILE_THREADS, [&] {
-            brick_tile_kernel<S, MASS, PAIR, 1, VT>(vals.data(), stride, start.data(), filled.data(), counter + 1, G, B, mesh1);
+            brick_tile_kernel<S, MASS, PAIR, 1, VT>(vals.data(), start.data(), filled.data(), counter + 1, G, B, mesh1);
         });
 }
 
