@@ -224,3 +224,12 @@ def test_the_harness_sees_a_missing_barrier(oracle_fast, tmp_path):
     got, _ = deposit(lib, pos, None, N, L, "tsc")
     want = oracle_fast.paint(pos, None, N, L, "tsc", 0.0)
     assert not np.allclose(got, want, rtol=0, atol=1e-3 * want.max())
+
+
+def test_rank_mod_three_expression_of_the_tile_kernel():
+    """brick_tile_kernel takes the rank of a lane among the lanes that start on its bank (0 .. 31) modulo 3 as
+    rank - 3 * ((rank * 11) >> 5) (three integer instructions instead of the compiler's ten for % 3): the expression
+    itself, and that it is still the one in the source."""
+    assert all(r - 3 * ((r * 11) >> 5) == r % 3 for r in range(32))
+    src = open(os.path.join(HERE, "..", "astrild_b200", "csrc", "deposit_sorted.cu")).read()
+    assert "rank - 3u * ((rank * 11u) >> 5)" in src
