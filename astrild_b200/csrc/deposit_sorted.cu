@@ -380,6 +380,9 @@ brick_tile_kernel(const VT *__restrict__ vals, const unsigned int *__restrict__ 
 
             // ---- one thread per particle; the next particle's loads are in flight while this one is deposited ----
             // (with the rotation every lane of a warp makes the same number of trips: it votes across the warp)
+            // (measured, call 36: the warp's 96 payload words loaded as three coalesced words per lane and handed to their
+            // owners with three shuffles -- 3 + 3 instead of 3 x 2.2 wavefronts -- is slower, 20.76 against 20.25 ms for
+            // both meshes: SHFL goes through the same pipe)
             unsigned int p = c0 + tid;
             VT nxt = {};
             if (p < c1) nxt = vals[p];
