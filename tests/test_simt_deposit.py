@@ -121,10 +121,11 @@ def test_float64_positions_cic(simt, oracle_fast):
 
 
 def test_clustered_cells_take_several_chunks(simt, oracle_fast):
-    """7000 particles in one brick (more than the 3072-particle shared-memory chunk), 4000 of them in one cell."""
+    """11000 particles in one brick (more than the 8191-particle chunk between two flushes of the tile: the second chunk
+    runs on a tile re-zeroed by the first flush), 6000 of them in one cell (ranks up to 31 in the rotation's vote)."""
     rng = np.random.default_rng(6)
     N, L = 32, 32.0
-    pos = np.concatenate([rng.random((3000, 3)) * [10.0, 5.0, 20.0] + 1.0, rng.random((4000, 3)) * 0.9 + [3.0, 3.0, 3.0],
+    pos = np.concatenate([rng.random((5000, 3)) * [10.0, 5.0, 20.0] + 1.0, rng.random((6000, 3)) * 0.9 + [3.0, 3.0, 3.0],
                           rng.random((500, 3)) * L]).astype(np.float32)
     a, b = deposit(simt, pos, None, N, L, "tsc", pair=True)
     close(a, oracle_fast.paint(pos, None, N, L, "tsc", 0.0))
