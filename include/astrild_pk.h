@@ -69,8 +69,9 @@ int apk_plan_ghost_planes(const apk_plan *plan, int *n_lo, int *n_hi);
 /* ---- per-kernel timing (CUDA events recorded inside the library, on the caller's stream) ---- */
 /* on != 0: apk_deposit / apk_bin_power bracket their kernels with events.                     */
 int apk_plan_enable_timing(apk_plan *plan, int on);
-/* last apk_deposit on this plan, ms: [0] count pass (0 with the one-pass partition), [1] clearing the cursors and
- * page table, [2] brick partition kernel, [3] tile kernel(s) (sorted path) or the atomic kernel.  Synchronises on the last event. */
+/* last apk_deposit on this plan, ms: [0] brick count pass, [1] segment sums + scan of the counts, [2] brick scatter
+ * pass, [3] tile kernel(s) (sorted path; both meshes of an interlaced pair) or the atomic kernel(s).  Synchronises on
+ * the last event. */
 int apk_plan_last_deposit_ms(apk_plan *plan, float ms[4]);
 /* last apk_bin_power on this binning, ms: [0] fused binning kernel, [1] fold of per-CTA copies  */
 int apk_binning_last_ms(apk_binning *binning, float ms[2]);
