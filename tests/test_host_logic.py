@@ -62,3 +62,32 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.AstrildPkError):
         _lib.load()
+
+
+def test_recorded_bench_lines_carry_the_contract_keys():
+    """The JSON lines bench.py printed on the GPU box at the end of the round (committed under profiles/) have every key the
+    measurement contract names -- a guard against a bench change that drops one (the bench itself needs a GPU)."""
+    import json
+    here = os.path.dirname(os.path.abspath(__file__))
+    rec = os.path.join(here, "..", "profiles", "r02_call32")
+    line = json.loads(open(os.path.join(rec, "bench_default.json")).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "check"):
+        assert key in line, key
+    assert "workload" in line["config"] and line["n_gpus"] == 1 and line["gpu_launches"] > 0
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+    assert line["e2e"]["h2d_bytes_per_step"] == 12 * line["config"]["particles"]          # x, y, z float32 columns
+    roof = line["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof)
+    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-12 and roof["traffic"] >= roof["algorithmic_bytes_per_launch"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"]) and line["cpu_baseline"]["kind"] == "port"
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(line["clocks"])
+    assert line["check"]["ok"] and line["check"]["modes_equal"] and line["check"]["max_rel_P"] <= 1e-4
+    # the stage split adds up to the step (CUDA events on one stream)
+    ms = line["stages"]["ms"]
+    assert abs(ms["deposit_stage"] + ms["fft"] + ms["bin_stage"] - line["ms_per_step"]) < 0.05 * line["ms_per_step"]
+    ref = json.loads(open(os.path.join(rec, "bench_reference.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["metric"] == line["metric"] and ref["unit"] == line["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["kind"] == "port"
+    assert {k: v for k, v in ref["config"].items() if k in ("workload", "particles", "mesh", "resampler", "interlaced", "compensated")} == \
+           {k: v for k, v in line["config"].items() if k in ("workload", "particles", "mesh", "resampler", "interlaced", "compensated")}
